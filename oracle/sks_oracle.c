@@ -1,0 +1,246 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU oracle for the batched SKS / ACA / ACA-rect
+ * path and the ACA-RANSAC scorer.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the
+ * product (libsks_cuda.so) never links, loads or calls it.
+ *
+ * Parity status:
+ *   SKS / ACA (fp32, fp64): PINNED -- bit-compared against the reference's own
+ *     C++ (MOD/ACA_SKS.cpp compiled in place into oracle/_ref/libsks_ref.so by
+ *     oracle/Makefile) in tests/test_oracle.py, against golden vectors produced
+ *     by that library (tests/golden/), and against the two veri_4Pts.m
+ *     known-answer cases.
+ *   ACA-rect: PINNED to ML/ACA_rect.m via the veri_4Pts.m rectangle KAT (fp64)
+ *     and to golden vectors obtained by executing
+ *     "PyTorch Codes/Modules_Runtime_Test.py":296-302 on torch-CPU
+ *     (tests/golden/make_golden.py).  No C++ version exists in the reference.
+ *   RANSAC scoring: PARITY UNPINNED -- the reference has no inlier test or model
+ *     selection (only the sampler precedent GPU.cu:52-78).  Hypotheses are the
+ *     pinned ACA; the scoring rule below is this project's own definition.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
+ */
+#include "sks_oracle.h"
+
+#include <math.h>
+#include <string.h>
+
+#define REAL float
+#define SUF(x) x##_f32
+#include "solver_body.inc"
+#undef REAL
+#undef SUF
+
+#define REAL double
+#define SUF(x) x##_f64
+#include "solver_body.inc"
+#undef REAL
+#undef SUF
+
+/* ------------------------------------------------------------------ batches */
+/* AoS batches: src[n][8], tar[n][8] -> H[n][9]  (the CPU reference's layout,
+ * MOD/ACA_SKS.cpp:24; the caller loop is CPU/main.cpp:87-114). */
+
+#define DEF_BATCH(NAME, T, ONE)                                                          \
+    void NAME(const T *src, const T *tar, T *H, int64_t n, int normalize)               \
+    {                                                                                    \
+        for (int64_t i = 0; i < n; ++i)                                                  \
+            ONE(src + 8 * i, tar + 8 * i, H + 9 * i, normalize);                         \
+    }
+
+DEF_BATCH(oracle_aca_f32, float, oracle_aca_one_f32)
+DEF_BATCH(oracle_aca_f64, double, oracle_aca_one_f64)
+DEF_BATCH(oracle_sks_f32, float, oracle_sks_one_f32)
+DEF_BATCH(oracle_sks_f64, double, oracle_sks_one_f64)
+
+/* M == NULL: one shared rectangle corner (mx,my); else per-sample M[n][2]
+ * (PyTorch Codes/Modules_Runtime_Test.py:302 reads M per sample while
+ * width/ratio come from sample 0, :33-35). */
+#define DEF_RECT(NAME, T, ONE)                                                           \
+    void NAME(const T *tar, const T *M, T mx, T my, T width, T ratio, T *H, int64_t n,   \
+              int normalize)                                                             \
+    {                                                                                    \
+        for (int64_t i = 0; i < n; ++i) {                                                \
+            T ax = M ? M[2 * i] : mx, ay = M ? M[2 * i + 1] : my;                        \
+            ONE(tar + 8 * i, ax, ay, width, ratio, H + 9 * i, normalize);                \
+        }                                                                                \
+    }
+
+DEF_RECT(oracle_aca_rect_f32, float, oracle_aca_rect_one_f32)
+DEF_RECT(oracle_aca_rect_f64, double, oracle_aca_rect_one_f64)
+
+/* Degeneracy flag: the reference never reports failure, it
+ * emits non-finite entries.  normalised: any of h[0..7] non-finite;
+ * up-to-scale: any of h[0..8] non-finite or h[8] == 0. */
+#define DEF_FLAGS(NAME, T)                                                               \
+    void NAME(const T *H, uint8_t *flag, int64_t n, int normalized)                      \
+    {                                                                                    \
+        for (int64_t i = 0; i < n; ++i) {                                                \
+            const T *h = H + 9 * i;                                                      \
+            int bad = 0;                                                                 \
+            for (int k = 0; k < 8; ++k)                                                  \
+                bad |= !isfinite(h[k]);                                                  \
+            if (!normalized)                                                             \
+                bad |= !isfinite(h[8]) || h[8] == (T)0;                                  \
+            flag[i] = (uint8_t)bad;                                                      \
+        }                                                                                \
+    }
+
+DEF_FLAGS(oracle_degenerate_f32, float)
+DEF_FLAGS(oracle_degenerate_f64, double)
+
+/* ------------------------------------------------- synthetic quad generator */
+/* Counter-based generator shared (as a specification) with the device
+ * generator in sks_homography_b200/csrc/synth.cu: value = mix(key(seed) ^
+ * (quad_index * G + lane)).  Distributions follow SURVEY.md 8(d):
+ *   dist 0  "deep"    : M = (U{10..29}, U{10..29}), 128-px source square in
+ *                       order TL,TR,BL,BR, target = source + 32*U[0,1)
+ *                       (PyTorch Codes/Modules_Runtime_Test.py:9-21, continuous)
+ *   dist 1  "image"   : 256-px square jittered by +-64 px inside a 1024x768
+ *                       frame, target = source +- 32 px (ML/veri_4Pts.m:35-36)
+ *   dist 2  "deep-int": dist 0 with integer offsets U{0..31} (exactly the
+ *                       reference's torch.randint generator). */
+
+static inline uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+uint64_t oracle_rng_u64(uint64_t seed, uint64_t ctr, uint32_t lane)
+{
+    const uint64_t key = mix64(seed + 0x9E3779B97F4A7C15ULL);
+    return mix64(key ^ (ctr * 0x9E3779B97F4A7C15ULL + (uint64_t)lane));
+}
+
+static inline uint32_t bounded(uint64_t r, uint32_t m)
+{
+    return (uint32_t)(((r >> 32) * (uint64_t)m) >> 32);
+}
+
+static inline float u01_f32(uint64_t r) { return (float)(r >> 40) * 0x1p-24f; }
+static inline double u01_f64(uint64_t r) { return (double)(r >> 11) * 0x1p-53; }
+
+#define DEF_SYNTH(NAME, T, U01)                                                          \
+    void NAME(T *src, T *tar, int64_t begin, int64_t count, uint64_t seed, int dist)     \
+    {                                                                                    \
+        static const int cx[4] = { 0, 1, 0, 1 }, cy[4] = { 0, 0, 1, 1 };                 \
+        for (int64_t j = 0; j < count; ++j) {                                            \
+            const uint64_t q = (uint64_t)(begin + j);                                    \
+            T *s = src + 8 * j, *t = tar + 8 * j;                                        \
+            if (dist == 1) {                                                             \
+                const T bx = (T)128 + (T)512 * U01(oracle_rng_u64(seed, q, 0));          \
+                const T by = (T)128 + (T)256 * U01(oracle_rng_u64(seed, q, 1));          \
+                for (int k = 0; k < 4; ++k) {                                            \
+                    const T px = bx + (T)(256 * cx[k]), py = by + (T)(256 * cy[k]);      \
+                    const T jx = (U01(oracle_rng_u64(seed, q, 2 + 2 * k)) - (T)0.5) * (T)128; \
+                    const T jy = (U01(oracle_rng_u64(seed, q, 3 + 2 * k)) - (T)0.5) * (T)128; \
+                    s[2 * k] = px + jx;                                                  \
+                    s[2 * k + 1] = py + jy;                                              \
+                    const T ox = (U01(oracle_rng_u64(seed, q, 10 + 2 * k)) - (T)0.5) * (T)64; \
+                    const T oy = (U01(oracle_rng_u64(seed, q, 11 + 2 * k)) - (T)0.5) * (T)64; \
+                    t[2 * k] = s[2 * k] + ox;                                            \
+                    t[2 * k + 1] = s[2 * k + 1] + oy;                                    \
+                }                                                                        \
+            } else {                                                                     \
+                const T mx = (T)(10 + bounded(oracle_rng_u64(seed, q, 0), 20));          \
+                const T my = (T)(10 + bounded(oracle_rng_u64(seed, q, 1), 20));          \
+                for (int k = 0; k < 4; ++k) {                                            \
+                    s[2 * k] = mx + (T)(128 * cx[k]);                                    \
+                    s[2 * k + 1] = my + (T)(128 * cy[k]);                                \
+                    const uint64_t rx = oracle_rng_u64(seed, q, 2 + 2 * k);              \
+                    const uint64_t ry = oracle_rng_u64(seed, q, 3 + 2 * k);              \
+                    const T ox = dist == 2 ? (T)bounded(rx, 32) : (T)32 * U01(rx);       \
+                    const T oy = dist == 2 ? (T)bounded(ry, 32) : (T)32 * U01(ry);       \
+                    t[2 * k] = s[2 * k] + ox;                                            \
+                    t[2 * k + 1] = s[2 * k + 1] + oy;                                    \
+                }                                                                        \
+            }                                                                            \
+        }                                                                                \
+    }
+
+DEF_SYNTH(oracle_synth_quads_f32, float, u01_f32)
+DEF_SYNTH(oracle_synth_quads_f64, double, u01_f64)
+
+/* ------------------------------------------------------------ ACA-RANSAC */
+/* Our own definition (parity unpinned, see header).
+ *   sample    : 4 indices per hypothesis, idx_k = u32(seed, pair*2^32 + hyp, k)
+ *               % n_pts -- "r % size" with repeats allowed, as GPU.cu:55-58;
+ *               or taken from an explicit sample list [n_hyp][4].
+ *   hypothesis: the pinned fp32 ACA, h33-normalised (MOD/ACA_SKS.cpp:24-102).
+ *   score     : forward transfer, division-free, every fused multiply-add
+ *               explicit so CPU and GPU agree bit for bit:
+ *                 u = fma(h0,x,fma(h1,y,h2)); v = fma(h3,x,fma(h4,y,h5));
+ *                 w = fma(h6,x,fma(h7,y,h8));
+ *                 du = fma(X,w,-u); dv = fma(Y,w,-v);
+ *                 e = fma(dv,dv,du*du); inlier <=> e < (thr2*w)*w
+ *   select    : key = count<<32 | (0xFFFFFFFF - hyp); best = max key
+ *               (highest count, lowest hypothesis id on ties). */
+
+uint32_t oracle_ransac_count_f32(const float *H, const float *corr, int32_t n_pts, float thr2)
+{
+    uint32_t cnt = 0;
+    for (int32_t i = 0; i < n_pts; ++i) {
+        const float x = corr[4 * i], y = corr[4 * i + 1];
+        const float X = corr[4 * i + 2], Y = corr[4 * i + 3];
+        const float u = fmaf(H[0], x, fmaf(H[1], y, H[2]));
+        const float v = fmaf(H[3], x, fmaf(H[4], y, H[5]));
+        const float w = fmaf(H[6], x, fmaf(H[7], y, H[8]));
+        const float du = fmaf(X, w, -u);
+        const float dv = fmaf(Y, w, -v);
+        const float e = fmaf(dv, dv, du * du);
+        const float lim = (thr2 * w) * w;
+        cnt += (e < lim) ? 1u : 0u;
+    }
+    return cnt;
+}
+
+void oracle_ransac_sample(uint64_t seed, int64_t pair, uint32_t hyp, int32_t n_pts,
+                          uint32_t idx[4])
+{
+    const uint64_t ctr = ((uint64_t)pair << 32) | (uint64_t)hyp;
+    for (uint32_t k = 0; k < 4; ++k)
+        idx[k] = (uint32_t)(oracle_rng_u64(seed, ctr, k) >> 32) % (uint32_t)n_pts;
+}
+
+void oracle_ransac_hypothesis_f32(const float *corr, const uint32_t idx[4], float *H)
+{
+    float s[8], t[8];
+    for (int k = 0; k < 4; ++k) {
+        const float *c = corr + 4 * (size_t)idx[k];
+        s[2 * k] = c[0];
+        s[2 * k + 1] = c[1];
+        t[2 * k] = c[2];
+        t[2 * k + 1] = c[3];
+    }
+    oracle_aca_one_f32(s, t, H, 1);
+}
+
+void oracle_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                           const uint32_t *samples, uint32_t hyp_begin, uint32_t hyp_count,
+                           uint32_t hyp_stride, uint64_t seed, float thr2, uint64_t *best_key,
+                           uint32_t *counts_out)
+{
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const float *c = corr + 4 * (size_t)n_pts * (size_t)p;
+        uint64_t best = 0;
+        for (uint32_t j = 0; j < hyp_count; ++j) {
+            const uint32_t hyp = hyp_begin + j;
+            uint32_t idx[4];
+            if (samples)
+                memcpy(idx, samples + 4 * ((size_t)p * hyp_stride + hyp), sizeof idx);
+            else
+                oracle_ransac_sample(seed, p, hyp, n_pts, idx);
+            float H[9];
+            oracle_ransac_hypothesis_f32(c, idx, H);
+            const uint32_t cnt = oracle_ransac_count_f32(H, c, n_pts, thr2);
+            if (counts_out)
+                counts_out[(size_t)p * hyp_count + j] = cnt;
+            const uint64_t key = ((uint64_t)cnt << 32) | (uint64_t)(0xFFFFFFFFu - hyp);
+            if (key > best)
+                best = key;
+        }
+        best_key[p] = best;
+    }
+}
