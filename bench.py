@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched 4-point homography path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic quadruples.
+Default workload = BASELINE.json configs[1]: batched ACA, general quad-to-quad,
+2^26 random quadruples per GPU, fp32, AoS in/out, h33-normalised (weak scaling:
+every rank solves its own contiguous 2^26-quad shard of the global index space,
+no data-path collective).  Rank 0 prints ONE JSON line.
+
+  value     whole-job homographies/s, inputs resident in HBM, CUDA-event timed
+  e2e       same metric through the host-pointer C ABI (sks_host_*): pinned host
+            buffers, H2D and D2H copies inside the timed region
+  roofline  algorithmic bytes (100 B/homography fp32 general) per
+            launch / mean launch duration, against the measured HBM copy peak
+  cpu_baseline  the reference's own C++ (oracle/_ref) on the host cores, bounded sample
+
+--impl reference times the reference's CPU implementation of the same path on
+the host cores (all hardware threads) and prints the same line with
+"impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ACA/SKS homographies/s"
+UNIT = "homographies/s"
+
+WORKLOADS = {
+    # name: (solver, dtype, bytes per homography (algorithmic), default log2 n, dist)
+    "aca_f32": ("aca", "f32", 100, 26, 0),     # BASELINE configs[1]  (headline)
+    "sks_f32": ("sks", "f32", 100, 26, 0),
+    "aca_f64": ("aca", "f64", 200, 25, 1),
+    "sks_f64": ("sks", "f64", 200, 25, 1),     # BASELINE configs[3]
+    "rect_f32": ("rect", "f32", 68, 26, 0),    # BASELINE configs[2] per-GPU shard at 4 GPUs
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload: str):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own C++ CPU path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle.oracle import Oracle, RefLib
+    solver, dt, bytes_per_h, log2n, dist = WORKLOADS[args.workload]
+    if solver == "rect":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has no C++ ACA-rect"}))
+        return 0
+    o = Oracle()
+    kind = "reference"
+    try:
+        ref = RefLib()
+        threads = ref.hardware_threads()
+        run = lambda s, t, out: ref.solve(solver, s, t, threads=threads, out=out)
+    except Exception:
+        kind, threads = "port", 1
+        run = lambda s, t, out: out.__setitem__(slice(None), o.solve(solver, s, t))
+    dtype = np.float32 if dt == "f32" else np.float64
+    S = 1 << args.ref_log2n
+    s, t = o.synth_quads(0, S, args.seed, dist, dtype)
+    out = np.empty((S, 9), dtype=dtype)
+    for _ in range(args.warmup):
+        run(s, t, out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(s, t, out)
+    el = time.perf_counter() - t0
+    value = S * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dt, "data": "synthetic",
+        "config": {"workload": f"{args.workload} AoS h33-normalised, reference C++ on host cores, "
+                               f"step = 2^{args.ref_log2n} distinct quadruples streamed from memory",
+                   "threads": threads, "compiler": "g++ -O2 -ffp-contract=off"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"2^{args.ref_log2n} quadruples per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="aca_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2n", type=int, default=None, help="quadruples per GPU = 2^log2n")
+    ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
+    ap.add_argument("--no-normalize", action="store_true")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--small-tile", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=4)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-log2n", type=int, default=None)
+    ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--ref-log2n", type=int, default=24)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 3)          # timing rules: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from sks_homography_b200 import api, lib
+    L = lib()
+    L.check(L.c.sks_cuda_set_variant(args.variant), "set_variant")
+    L.check(L.c.sks_cuda_set_tuning(args.small_tile, args.stages, args.ctas), "set_tuning")
+
+    solver, dt, bytes_per_h, log2n, dist_id = WORKLOADS[args.workload]
+    log2n = args.log2n if args.log2n is not None else log2n
+    n = 1 << log2n
+    tdt = torch.float32 if dt == "f32" else torch.float64
+    normalize = not args.no_normalize
+    begin = rank * n                                  # this rank's shard of the global index space
+
+    # ---- inputs resident in HBM, generated on the device -----------------------
+    src, tar = api.synth_quads(n, seed=args.seed, dist=dist_id, dtype=tdt, device=dev, begin=begin,
+                               layout=args.layout)
+    H = torch.empty((n, 9) if args.layout == "aos" else (9, n), dtype=tdt, device=dev)
+
+    def step():
+        if solver == "rect":
+            api.aca_rect(tar, 128.0, 1.0, 15.0, 12.0, result=H, normalize=normalize, layout=args.layout)
+        else:
+            api.solve(solver, src, tar, result=H, normalize=normalize, layout=args.layout)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.c.sks_cuda_reset_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    launches = int(L.c.sks_cuda_launch_count())
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if sampler else None
+    barrier()
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    peak, peak_src = peaks()
+    mean_launch_ms = statistics.mean(per_launch_ms)
+    achieved = n * bytes_per_h / (mean_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                "peak_source": peak_src, "bytes_per_homography": bytes_per_h,
+                "launch_ms_mean": mean_launch_ms, "launch_ms_min": min(per_launch_ms),
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- end to end through the host-pointer C ABI ------------------------------
+    e2e = None
+    if not args.no_e2e and args.layout == "aos":
+        ne = 1 << (args.e2e_log2n if args.e2e_log2n is not None else log2n)
+        ne = min(ne, n)
+        hs = torch.empty((ne, 8), dtype=tdt, pin_memory=True)
+        ht = torch.empty((ne, 8), dtype=tdt, pin_memory=True)
+        hH = torch.empty((ne, 9), dtype=tdt, pin_memory=True)
+        hs.copy_(src[:ne]); ht.copy_(tar[:ne])
+        torch.cuda.synchronize()
+
+        def host_step():
+            if solver == "rect":
+                api.aca_rect(ht, 128.0, 1.0, 15.0, 12.0, result=hH, normalize=normalize)
+            else:
+                api.solve(solver, hs, ht, result=hH, normalize=normalize)
+
+        host_step()                                   # warm-up: ring buffers, streams
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()                               # synchronous: returns with H in host memory
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        esz = 4 if dt == "f32" else 8
+        in_elems = 8 if solver == "rect" else 16
+        e2e = {"value": world * ne * args.e2e_steps / el, "unit": UNIT,
+               "h2d_bytes_per_step": ne * in_elems * esz, "d2h_bytes_per_step": ne * 9 * esz,
+               "steps": args.e2e_steps, "quadruples_per_step_per_gpu": ne,
+               "api": "sks_host_* (pinned host buffers, chunked H2D/kernel/D2H ring)"}
+        # the host path must give the same bytes as the device path
+        if not torch.equal(hH.view(torch.int32 if dt == "f32" else torch.int64),
+                           H[:ne].cpu().view(torch.int32 if dt == "f32" else torch.int64)):
+            same_nan = torch.equal(torch.isnan(hH), torch.isnan(H[:ne].cpu()))
+            e2e["parity_vs_device_path"] = "nan-pattern-equal" if same_nan else "MISMATCH"
+        else:
+            e2e["parity_vs_device_path"] = "bit-exact"
+        del hs, ht, hH
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the reference's own C++ ---------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and args.layout == "aos" and solver != "rect":
+        from oracle.oracle import Oracle, RefLib
+        S = min(n, 1 << args.cpu_log2n)
+        s_h, t_h = src[:S].cpu().numpy(), tar[:S].cpu().numpy()
+        out = np.empty((S, 9), dtype=s_h.dtype)
+        try:
+            ref = RefLib()
+            threads, kind = ref.hardware_threads(), "reference"
+            run = lambda: ref.solve(solver, s_h, t_h, threads=threads, out=out)
+        except Exception:
+            o = Oracle()
+            threads, kind = 1, "port"
+            run = lambda: out.__setitem__(slice(None), o.solve(solver, s_h, t_h))
+        run()
+        best = 1e30
+        for _ in range(5):
+            t0 = time.perf_counter(); run(); best = min(best, time.perf_counter() - t0)
+        got = H[:S].cpu().numpy() if normalize else None
+        parity = None
+        if got is not None:
+            v = np.uint32 if dt == "f32" else np.uint64
+            ok = (got.view(v) == out.view(v)) | (np.isnan(got) & np.isnan(out))
+            parity = {"checked_quadruples": int(S), "mismatching_elements": int((~ok).sum())}
+        cpu = {"value": S / best, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"first 2^{args.cpu_log2n} quadruples of the workload, best of 5 passes, "
+                         f"MOD/ACA_SKS.cpp g++ -O2 -ffp-contract=off, {threads} threads",
+               "parity_gpu_vs_cpu": parity}
+
+    if rank == 0:
+        line = {
+            "impl": "ours", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dt,
+            "data": "synthetic",
+            "config": {"workload": f"batched {solver.upper()} {dt} 2^{log2n} quadruples per GPU, "
+                                   f"{args.layout.upper()} in/out, "
+                                   f"{'h33-normalised' if normalize else 'up to scale'}",
+                       "quadruples_per_gpu": n, "layout": args.layout, "variant": args.variant,
+                       "l2": f"inputs+outputs {n * bytes_per_h / 1e9:.2f} GB per step >> 126 MB L2, no flush needed",
+                       "seed": args.seed, "dist": dist_id},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,184 @@
+/*
+ * libsks_cuda -- C ABI of the B200-native batched 4-point homography engine.
+ *
+ * This is the drop-in boundary for the batched SKS / ACA / ACA-rect path of
+ * cscvlab/SKS-Homography.  The reference has no FFI layer of its own; its
+ * boundary is four C++ free functions, two CUDA kernels with host wrappers,
+ * two Python functions and one MATLAB function.  Each entry point below names
+ * the reference interface it replaces ("MOD/" = "C++ Codes/modules/",
+ * "GPU.cu" = "C++ Codes/Runtime Test/GPU_Runtime Test/GPU_Runtime Test.cu",
+ * "PY.py" = "PyTorch Codes/Modules_Runtime_Test.py", "ML/" = "Matlab Codes/").
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - return 0 on success (the reference's solvers always return 0,
+ *     MOD/ACA_SKS.cpp:101,178,302,417); <0 = SKS_ERR_*, >0 = cudaError_t.
+ *   - numerical degeneracy is NOT an error: exactly like the reference it shows
+ *     up as non-finite entries of H and, if requested, in the
+ *     optional per-quadruple `degenerate` byte array.
+ *   - the sks_cuda_* functions take DEVICE pointers, enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream) and
+ *     return without synchronising.  The sks_host_* functions take HOST
+ *     pointers (what the reference's C++ functions take) and return when the
+ *     result is in the caller's buffer.
+ *   - there is no CPU fallback and no backend dispatch: without a CUDA device
+ *     every compute entry point fails with SKS_ERR_NO_DEVICE / a cudaError_t.
+ *   - arithmetic reproduces the reference's operation order with fused
+ *     multiply-add contraction disabled, so results are bit-identical to the
+ *     reference's C++ built with -ffp-contract=off.
+ *   - all base pointers must be 16-byte aligned (cudaMalloc gives 256).
+ *
+ * Layouts (per quadruple i of n; points M,N,P,Q as x0,y0,x1,y1,x2,y2,x3,y3)
+ *   SKS_LAYOUT_AOS  src[i*8+k], tar[i*8+k], H[i*9+k]       (MOD/ACA_SKS.cpp:24)
+ *   SKS_LAYOUT_SOA  src[k*ld+i], tar[k*ld+i], H[k*ld+i]    (GPU.cu:87-95,141-149)
+ *                   ld = leading stride in elements, 0 means n; 64-bit offsets
+ *                   (the reference's `int` offsets overflow beyond 2^31/9).
+ */
+#ifndef SKS_CUDA_H
+#define SKS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKS_CUDA_ABI_VERSION 1
+
+enum { SKS_OK = 0, SKS_ERR_INVALID_ARG = -1, SKS_ERR_UNALIGNED = -2, SKS_ERR_NO_DEVICE = -3 };
+enum { SKS_LAYOUT_AOS = 0, SKS_LAYOUT_SOA = 1 };
+enum {
+    SKS_FLAG_NORMALIZE = 1 /* divide out h33 as MOD/ACA_SKS.cpp:94-98 does; without it the
+                              result is up to scale as in GPU.cu:141-149 / PY.py:372-381 */
+};
+enum { SKS_DIST_DEEP = 0, SKS_DIST_IMAGE = 1, SKS_DIST_DEEP_INT = 2 };
+
+int sks_cuda_abi_version(void);
+const char *sks_cuda_error_string(int status);
+int sks_cuda_device_count(int *count);
+
+/* ---- streaming solvers, device pointers --------------------------------- */
+/* replaces sks::runKernel_ACA            MOD/ACA_SKS.hpp:17, MOD/ACA_SKS.cpp:24-102
+ *          cal_Homo_ACA / cal_ACA (SoA)  GPU.cu:81-151, :1166-1206
+ *          ACA_vanilla                   PY.py:312-388                        */
+int sks_cuda_aca_f32(const float *src, const float *tar, float *H, int64_t n, int layout,
+                     int64_t ld, int flags, uint8_t *degenerate, void *stream);
+/* replaces sks::runKernel_ACA_double     MOD/ACA_SKS.hpp:18, MOD/ACA_SKS.cpp:104-179 */
+int sks_cuda_aca_f64(const double *src, const double *tar, double *H, int64_t n, int layout,
+                     int64_t ld, int flags, uint8_t *degenerate, void *stream);
+/* replaces sks::runKernel_SKS            MOD/ACA_SKS.hpp:19, MOD/ACA_SKS.cpp:189-303 */
+int sks_cuda_sks_f32(const float *src, const float *tar, float *H, int64_t n, int layout,
+                     int64_t ld, int flags, uint8_t *degenerate, void *stream);
+/* replaces sks::runKernel_SKS_double     MOD/ACA_SKS.hpp:20, MOD/ACA_SKS.cpp:305-418
+ *          cal_Homo_SKS / cal_SKS (SoA)  GPU.cu:153-240, :1208-1243              */
+int sks_cuda_sks_f64(const double *src, const double *tar, double *H, int64_t n, int layout,
+                     int64_t ld, int flags, uint8_t *degenerate, void *stream);
+
+/* replaces ACA_rect(TargetPts, M_x, M_y, width, ratio_rec)  ML/ACA_rect.m:22-38
+ *          TensorACA_rect(bs, src, tar, scale, div)         PY.py:286-309
+ * tar holds the 4 target corners TL,TR,BL,BR (8 values per quadruple, the
+ * homogeneous 1-row of the reference's 3x4 matrices is implied).  The source
+ * rectangle (top-left (mx,my), width, ratio = width/height) is shared by the
+ * batch; if M != NULL it supplies a per-quadruple top-left corner
+ * (AoS M[i*2+k], SoA M[k*ld+i]) as PY.py:302 does, and mx,my are ignored.
+ * With SKS_FLAG_NORMALIZE every element is DIVIDED by h33 (ML/ACA_rect.m:36). */
+int sks_cuda_aca_rect_f32(const float *tar, const float *M, float mx, float my, float width,
+                          float ratio, float *H, int64_t n, int layout, int64_t ld, int flags,
+                          uint8_t *degenerate, void *stream);
+int sks_cuda_aca_rect_f64(const double *tar, const double *M, double mx, double my,
+                          double width, double ratio, double *H, int64_t n, int layout,
+                          int64_t ld, int flags, uint8_t *degenerate, void *stream);
+
+/* ---- host-pointer entry points (what the reference's C++ callers hold) ---- */
+/* Drop-in for the loop `for (k...) sks::runKernel_*(src, tar, result)` of
+ * CPU/main.cpp:87-114 over n quadruples: AoS host buffers in, AoS host buffer
+ * out, always on the current device, chunked and double-buffered so H2D copy,
+ * kernel and D2H copy overlap.  Pinned (cudaHostAlloc / cudaHostRegister)
+ * buffers are copied directly; pageable ones go through an internal pinned
+ * ring.  flags as above. */
+int sks_host_aca_f32(const float *src, const float *tar, float *H, int64_t n, int flags);
+int sks_host_aca_f64(const double *src, const double *tar, double *H, int64_t n, int flags);
+int sks_host_sks_f32(const float *src, const float *tar, float *H, int64_t n, int flags);
+int sks_host_sks_f64(const double *src, const double *tar, double *H, int64_t n, int flags);
+int sks_host_aca_rect_f32(const float *tar, const float *M, float mx, float my, float width,
+                          float ratio, float *H, int64_t n, int flags);
+int sks_host_aca_rect_f64(const double *tar, const double *M, double mx, double my,
+                          double width, double ratio, double *H, int64_t n, int flags);
+/* pinned host allocation helpers for callers that want the zero-staging path */
+int sks_host_alloc_pinned(void **ptr, int64_t bytes);
+int sks_host_free_pinned(void *ptr);
+
+/* ---- minimal-sample gather (hypothesis generation from a match pool) ------ */
+/* replaces get_rand_list  GPU.cu:52-78 (+ host setup :1443-1451): for each of
+ * n hypotheses pick 4 correspondences r_k % pool_size (repeats allowed) from a
+ * pool of (x,y,X,Y) matches and emit src/tar quadruples.  rand4 is
+ * [4][n] uint32 as the reference's cuRAND buffer; NULL = counter RNG(seed). */
+int sks_cuda_gather_samples_f32(const float *pool_xyXY, uint32_t pool_size,
+                                const uint32_t *rand4, uint64_t seed, float *src, float *tar,
+                                int64_t n, int layout, int64_t ld, void *stream);
+int sks_cuda_gather_samples_f64(const double *pool_xyXY, uint32_t pool_size,
+                                const uint32_t *rand4, uint64_t seed, double *src, double *tar,
+                                int64_t n, int layout, int64_t ld, void *stream);
+
+/* ---- fused ACA-RANSAC ----------------------------------------------------- */
+/* New (nothing like it in the reference; sampler precedent GPU.cu:52-78).
+ * corr: [n_pairs][n_pts][4] = (x,y,X,Y) fp32.  Hypothesis ids
+ * [hyp_begin, hyp_begin+hyp_count) of every pair are generated (4 indices
+ * u32 % n_pts from the counter RNG keyed (seed, pair, hyp), or read from
+ * samples[n_pairs][hyp_stride][4] if non-NULL), solved with the bit-exact fp32
+ * ACA, scored against the pair's correspondences held in shared memory and
+ * reduced to best_key[pair] = max(count<<32 | (0xFFFFFFFF - hyp)).  best_key
+ * is MAX-combined into the caller's array (zero it before the first call), so
+ * several calls / several GPUs can cover disjoint hypothesis ranges and be
+ * merged with an integer max-reduce.  No per-hypothesis H touches HBM. */
+int sks_cuda_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                            const uint32_t *samples, uint32_t hyp_stride, uint32_t hyp_begin,
+                            uint32_t hyp_count, uint64_t seed, float thr2,
+                            unsigned long long *best_key, void *stream);
+/* Recompute the winning model of every pair from best_key (the sample list is
+ * a pure function of the seed, so no H ever travels between GPUs): H_best
+ * [n_pairs][9], inlier_count [n_pairs], optional inlier_mask [n_pairs][n_pts]. */
+int sks_cuda_ransac_finalize_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                                 const uint32_t *samples, uint32_t hyp_stride, uint64_t seed,
+                                 float thr2, const unsigned long long *best_key, float *H_best,
+                                 uint32_t *inlier_count, uint8_t *inlier_mask, void *stream);
+
+/* ---- synthetic inputs (bench / tests), generated on the device ------------ */
+/* Counter-based generator, bit-identical to oracle_synth_quads_* for the same
+ * (seed, dist); distributions per SURVEY.md 8(d) (PY.py:9-21, ML/veri_4Pts.m). */
+int sks_cuda_synth_quads_f32(float *src, float *tar, int64_t begin, int64_t count,
+                             uint64_t seed, int dist, int layout, int64_t ld, void *stream);
+int sks_cuda_synth_quads_f64(double *src, double *tar, int64_t begin, int64_t count,
+                             uint64_t seed, int dist, int layout, int64_t ld, void *stream);
+/* RANSAC scene: per pair a ground-truth homography from a SKS_DIST_DEEP quad,
+ * inlier_permille of the points follow it with +-noise px uniform noise, the
+ * rest are uniform outliers in the 160x160 frame. */
+int sks_cuda_synth_corr_f32(float *corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
+                            uint64_t seed, int inlier_permille, float noise, void *stream);
+
+/* ---- multi-GPU helpers ----------------------------------------------------- */
+/* Contiguous shard [begin, begin+count) of n units for `rank` of `world`
+ * (SURVEY.md 8(e)); the streaming solvers need no collective at all. */
+int sks_cuda_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *count);
+
+/* ---- introspection / tuning ------------------------------------------------ */
+/* Number of kernels this library has launched in this process since the last
+ * reset (bench.py reports it as gpu_launches). */
+int64_t sks_cuda_launch_count(void);
+void sks_cuda_reset_launch_count(void);
+/* Kernel variant for the AoS streaming solvers: 0 = default (best measured),
+ * 1 = direct vector loads + shared-memory transposed stores,
+ * 2 = persistent TMA bulk-copy ring (cp.async.bulk + mbarrier).  A tuning knob
+ * for bench.py sweeps, not a backend switch: every variant is sm_100a CUDA. */
+int sks_cuda_set_variant(int variant);
+int sks_cuda_get_variant(void);
+/* Ring-kernel tuning: small_tile (0: 256 fp32 / 128 fp64 quadruples per tile,
+ * 1: half of that), stages (2..16 shared-memory ring slots), ctas_per_sm
+ * (0 = as many as fit). */
+int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm);
+int sks_cuda_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKS_CUDA_H */

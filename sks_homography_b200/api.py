@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference's solver interface over libsks_cuda.
+
+Names and argument meaning follow the reference so its callers (and our parity
+tests) read the same:
+
+  runKernel_ACA / _ACA_double / _SKS / _SKS_double   MOD/ACA_SKS.hpp:17-20
+      (src, tar, result) with AoS points x0,y0,..,x3,y3 -> row-major 3x3,
+      h33-normalised, returns 0.  Here src/tar/result are batches [n,8]/[n,9].
+  ACA_rect(TargetPts, M_x, M_y, width, ratio_rec)    ML/ACA_rect.m:22
+  TensorACA_rect(bs, src, tar, scale, div)           PY.py:286  (returns H, un-normalised)
+  ACA_vanilla(bs, src, tar)                          PY.py:312  (returns H, un-normalised)
+
+torch is used for memory and streams only.  CUDA tensors go straight to the
+device-pointer C ABI on the current stream; CPU tensors go through the
+host-pointer C ABI (sks_host_*), i.e. they are still solved on the GPU.  There
+is no CPU compute path: without the library or a GPU every call raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import FLAG_NORMALIZE, LAYOUT_AOS, LAYOUT_SOA, lib
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _check_pair(src, tar, dtype):
+    if src.dtype != dtype or tar.dtype != dtype:
+        raise TypeError(f"expected {dtype} tensors, got {src.dtype}/{tar.dtype}")
+    if src.device != tar.device:
+        raise ValueError("src and tar must live on the same device")
+
+
+def solve(solver: str, src: torch.Tensor, tar: torch.Tensor, result: torch.Tensor | None = None,
+          normalize: bool = True, layout: str = "aos", degenerate: torch.Tensor | None = None
+          ) -> torch.Tensor:
+    """Batched general 4-point solve.  solver in {'aca','sks'}.
+
+    aos: src/tar [n,8] (or [n,4,2]) -> H [n,9];  soa: src/tar [8,n] -> H [9,n].
+    """
+    dtype = src.dtype
+    if dtype not in _SUFFIX:
+        raise TypeError("float32 or float64 only")
+    _check_pair(src, tar, dtype)
+    L = lib()
+    src, tar = src.contiguous(), tar.contiguous()
+    if layout == "aos":
+        n = src.numel() // 8
+        shape, lay, ld = (n, 9), LAYOUT_AOS, 0
+    elif layout == "soa":
+        if src.dim() != 2 or src.shape[0] != 8:
+            raise ValueError("soa layout expects [8, n]")
+        n = src.shape[1]
+        shape, lay, ld = (9, n), LAYOUT_SOA, n
+    else:
+        raise ValueError(layout)
+    if result is None:
+        result = torch.empty(shape, dtype=dtype, device=src.device)
+    elif result.numel() != 9 * n or result.dtype != dtype or not result.is_contiguous():
+        raise ValueError("result must be a contiguous tensor of 9*n elements")
+    flags = FLAG_NORMALIZE if normalize else 0
+    name = f"{solver}_{_SUFFIX[dtype]}"
+    if src.is_cuda:
+        with torch.cuda.device(src.device):
+            fn = getattr(L.c, f"sks_cuda_{name}")
+            L.check(fn(_ptr(src), _ptr(tar), _ptr(result), n, lay, ld, flags, _ptr(degenerate),
+                       _stream_ptr(src)), f"sks_cuda_{name}")
+    else:
+        if layout != "aos" or degenerate is not None:
+            raise ValueError("host tensors: AoS layout without flag output only")
+        fn = getattr(L.c, f"sks_host_{name}")
+        L.check(fn(_ptr(src), _ptr(tar), _ptr(result), n, flags), f"sks_host_{name}")
+    return result
+
+
+def runKernel_ACA(src, tar, result=None, **kw):
+    _check_pair(src, tar, torch.float32)
+    return solve("aca", src, tar, result, **kw)
+
+
+def runKernel_ACA_double(src, tar, result=None, **kw):
+    _check_pair(src, tar, torch.float64)
+    return solve("aca", src, tar, result, **kw)
+
+
+def runKernel_SKS(src, tar, result=None, **kw):
+    _check_pair(src, tar, torch.float32)
+    return solve("sks", src, tar, result, **kw)
+
+
+def runKernel_SKS_double(src, tar, result=None, **kw):
+    _check_pair(src, tar, torch.float64)
+    return solve("sks", src, tar, result, **kw)
+
+
+def aca_rect(tar: torch.Tensor, width: float, ratio: float, M_x: float = 0.0, M_y: float = 0.0,
+             M: torch.Tensor | None = None, result: torch.Tensor | None = None,
+             normalize: bool = True, layout: str = "aos",
+             degenerate: torch.Tensor | None = None) -> torch.Tensor:
+    """ACA-rect on interleaved target corners tar [n,8] (TL,TR,BL,BR)."""
+    dtype = tar.dtype
+    if dtype not in _SUFFIX:
+        raise TypeError("float32 or float64 only")
+    L = lib()
+    tar = tar.contiguous()
+    if layout == "aos":
+        n = tar.numel() // 8
+        shape, lay, ld = (n, 9), LAYOUT_AOS, 0
+    else:
+        n = tar.shape[1]
+        shape, lay, ld = (9, n), LAYOUT_SOA, n
+    if M is not None:
+        M = M.contiguous()
+        if M.dtype != dtype or M.numel() != 2 * n:
+            raise ValueError("M must hold 2*n values of tar's dtype")
+    if result is None:
+        result = torch.empty(shape, dtype=dtype, device=tar.device)
+    flags = FLAG_NORMALIZE if normalize else 0
+    name = f"aca_rect_{_SUFFIX[dtype]}"
+    if tar.is_cuda:
+        with torch.cuda.device(tar.device):
+            fn = getattr(L.c, f"sks_cuda_{name}")
+            L.check(fn(_ptr(tar), _ptr(M), M_x, M_y, width, ratio, _ptr(result), n, lay, ld, flags,
+                       _ptr(degenerate), _stream_ptr(tar)), f"sks_cuda_{name}")
+    else:
+        if layout != "aos" or degenerate is not None:
+            raise ValueError("host tensors: AoS layout without flag output only")
+        fn = getattr(L.c, f"sks_host_{name}")
+        L.check(fn(_ptr(tar), _ptr(M), M_x, M_y, width, ratio, _ptr(result), n, flags),
+                f"sks_host_{name}")
+    return result
+
+
+def ACA_rect(TargetPts: torch.Tensor, M_x: float, M_y: float, width: float, ratio_rec: float
+             ) -> torch.Tensor:
+    """MATLAB signature (ML/ACA_rect.m:22): TargetPts is 3x4 (or [bs,3,4])
+    homogeneous, columns TL,TR,BL,BR; returns the h33-normalised 3x3."""
+    single = TargetPts.dim() == 2
+    T = TargetPts.reshape(-1, 3, 4)
+    tar = T[:, :2, :].transpose(1, 2).reshape(-1, 8)
+    H = aca_rect(tar, width, ratio_rec, M_x, M_y, normalize=True).reshape(-1, 3, 3)
+    return H[0] if single else H
+
+
+def TensorACA_rect(bs: int, src: torch.Tensor, tar: torch.Tensor, scale, div) -> torch.Tensor:
+    """PY.py:286-309 with the tensor conventions of PY.py:24-37: src/tar are
+    [bs,3,4] homogeneous (rows x,y,1; columns TL,TR,BL,BR); scale = width and
+    div = width/height of the shared source square; the per-sample corner is
+    src[:, 0:2, 0] (PY.py:302).  Returns the un-normalised H [bs,3,3] that the
+    reference computes and discards."""
+    tarq = tar[:, :2, :].transpose(1, 2).reshape(bs, 8)
+    M = src[:, :2, 0].contiguous()
+    H = aca_rect(tarq, float(scale), float(div), M=M, normalize=False)
+    return H.reshape(bs, 3, 3)
+
+
+def ACA_vanilla(bs: int, src: torch.Tensor, tar: torch.Tensor) -> torch.Tensor:
+    """PY.py:312-388: src/tar [bs,4,2] -> un-normalised H [bs,3,3]."""
+    H = solve("aca", src.reshape(bs, 8), tar.reshape(bs, 8), normalize=False)
+    return H.reshape(bs, 3, 3)
+
+
+# ------------------------------------------------------------ synthetic data
+def synth_quads(n: int, seed: int = 11, dist: int = _lib.DIST_DEEP, dtype=torch.float32,
+                device="cuda", begin: int = 0, layout: str = "aos"):
+    """Device-generated quadruples [begin, begin+n) (bit-identical to the oracle's)."""
+    L = lib()
+    dev = torch.device(device)
+    shape = (n, 8) if layout == "aos" else (8, n)
+    src = torch.empty(shape, dtype=dtype, device=dev)
+    tar = torch.empty(shape, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        fn = getattr(L.c, f"sks_cuda_synth_quads_{_SUFFIX[dtype]}")
+        L.check(fn(_ptr(src), _ptr(tar), begin, n, seed, dist,
+                   LAYOUT_AOS if layout == "aos" else LAYOUT_SOA, n, _stream_ptr(src)),
+                "sks_cuda_synth_quads")
+    return src, tar
+
+
+def synth_corr(n_pairs: int, n_pts: int, seed: int = 11, inlier_permille: int = 500,
+               noise: float = 0.5, device="cuda", pair_begin: int = 0) -> torch.Tensor:
+    L = lib()
+    dev = torch.device(device)
+    corr = torch.empty((n_pairs, n_pts, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.c.sks_cuda_synth_corr_f32(_ptr(corr), pair_begin, n_pairs, n_pts, seed,
+                                            inlier_permille, noise, _stream_ptr(corr)),
+                "sks_cuda_synth_corr_f32")
+    return corr
+
+
+def gather_samples(pool: torch.Tensor, n: int, seed: int = 11, rand4: torch.Tensor | None = None,
+                   layout: str = "aos"):
+    """GPU.cu:52-78: n minimal samples from a match pool [size,4] = (x,y,X,Y)."""
+    L = lib()
+    dtype = pool.dtype
+    pool = pool.contiguous()
+    shape = (n, 8) if layout == "aos" else (8, n)
+    src = torch.empty(shape, dtype=dtype, device=pool.device)
+    tar = torch.empty(shape, dtype=dtype, device=pool.device)
+    with torch.cuda.device(pool.device):
+        fn = getattr(L.c, f"sks_cuda_gather_samples_{_SUFFIX[dtype]}")
+        L.check(fn(_ptr(pool), pool.shape[0], _ptr(rand4), seed, _ptr(src), _ptr(tar), n,
+                   LAYOUT_AOS if layout == "aos" else LAYOUT_SOA, n, _stream_ptr(pool)),
+                "sks_cuda_gather_samples")
+    return src, tar
+
+
+# ------------------------------------------------------------------- RANSAC
+def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
+                samples: torch.Tensor | None = None, hyp_begin: int = 0,
+                hyp_count: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Score hypothesis ids [hyp_begin, hyp_begin+hyp_count) of every pair and
+    max-combine into `out` (int64 view of the packed uint64 keys)."""
+    L = lib()
+    corr = corr.contiguous()
+    P, n_pts, _ = corr.shape
+    hyp_count = n_hyp - hyp_begin if hyp_count is None else hyp_count
+    if out is None:
+        out = torch.zeros(P, dtype=torch.int64, device=corr.device)
+    with torch.cuda.device(corr.device):
+        L.check(L.c.sks_cuda_ransac_aca_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, hyp_begin,
+                                            hyp_count, seed, thr2, _ptr(out), _stream_ptr(corr)),
+                "sks_cuda_ransac_aca_f32")
+    return out
+
+
+def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys: torch.Tensor,
+                    samples: torch.Tensor | None = None, want_mask: bool = False):
+    L = lib()
+    corr = corr.contiguous()
+    P, n_pts, _ = corr.shape
+    H = torch.empty((P, 9), dtype=torch.float32, device=corr.device)
+    cnt = torch.empty(P, dtype=torch.int32, device=corr.device)
+    mask = torch.empty((P, n_pts), dtype=torch.uint8, device=corr.device) if want_mask else None
+    with torch.cuda.device(corr.device):
+        L.check(L.c.sks_cuda_ransac_finalize_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed,
+                                                 thr2, _ptr(keys), _ptr(H), _ptr(cnt), _ptr(mask),
+                                                 _stream_ptr(corr)),
+                "sks_cuda_ransac_finalize_f32")
+    return H, cnt, mask
+
+
+def decode_keys(keys: torch.Tensor):
+    """packed key -> (inlier count, hypothesis id)"""
+    count = keys >> 32
+    hyp = 0xFFFFFFFF - (keys & 0xFFFFFFFF)
+    return count, hyp

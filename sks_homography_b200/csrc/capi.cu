@@ -1,0 +1,342 @@
+// libsks_cuda: the C ABI (include/sks_cuda.h) over the sm_100a kernels.
+// Device-pointer entry points only enqueue work; nothing here synchronises,
+// allocates per call, or falls back to the CPU.
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sks_cuda.h"
+#include "ransac.cuh"
+#include "stream_kernels.cuh"
+#include "synth.cuh"
+
+using namespace sksb;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_variant{0};        // 0 default, 1 direct, 2 ring
+std::atomic<int> g_tile_small{0};     // ring tile: 0 = 256/128 (f32/f64), 1 = 128/64
+std::atomic<int> g_stages{4};
+std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
+
+struct DevInfo {
+    int sms = 0;
+    int smem_optin = 0;
+    bool ok = false;
+};
+
+int device_info(DevInfo& out)
+{
+    static DevInfo cache[64];
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SKS_ERR_NO_DEVICE : (int)e;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    DevInfo& d = cache[dev & 63];
+    if (!d.ok) {
+        if ((e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+            return (int)e;
+        if ((e = cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+            return (int)e;
+        d.ok = true;
+    }
+    out = d;
+    return SKS_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int finish_launch()
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SKS_OK : (int)e;
+}
+
+template <int SOLVER, typename T, int TILE>
+int launch_ring(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, uint8_t* degen,
+                int64_t n, bool normalize, const DevInfo& dev, cudaStream_t st)
+{
+    using L = RingLayout<SOLVER, T, TILE>;
+    auto kern = k_aos_ring<SOLVER, T, TILE>;
+    int stages = g_stages.load();
+    if (stages < 2) stages = 2;
+    while (stages > 2 && L::smem_bytes(stages) > dev.smem_optin) --stages;
+    const int smem = L::smem_bytes(stages);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    const int want = g_ctas_per_sm.load();
+    if (want > 0 && want < occ) occ = want;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int64_t grid = n_tiles < (int64_t)dev.sms * occ ? n_tiles : (int64_t)dev.sms * occ;
+    kern<<<(unsigned)grid, TILE, smem, st>>>(src, tar, M, rp, H, degen, n, stages, normalize);
+    return finish_launch();
+}
+
+template <int SOLVER, typename T>
+int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, int64_t n,
+                  int layout, int64_t ld, int flags, uint8_t* degen, void* stream)
+{
+    if (n < 0 || H == nullptr || tar == nullptr) return SKS_ERR_INVALID_ARG;
+    if (SOLVER != SOLVER_RECT && src == nullptr) return SKS_ERR_INVALID_ARG;
+    if (layout != SKS_LAYOUT_AOS && layout != SKS_LAYOUT_SOA) return SKS_ERR_INVALID_ARG;
+    if (flags & ~SKS_FLAG_NORMALIZE) return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n == 0) return SKS_OK;
+    if (!aligned16(H) || !aligned16(tar) || (src && !aligned16(src)) || (M && !aligned16(M)))
+        return SKS_ERR_UNALIGNED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool normalize = (flags & SKS_FLAG_NORMALIZE) != 0;
+
+    if (layout == SKS_LAYOUT_SOA) {
+        if (ld == 0) ld = n;
+        if (ld < n) return SKS_ERR_INVALID_ARG;
+        constexpr int THREADS = 128;
+        constexpr int Q = ChunkTraits<T>::EPC;
+        if (ld % Q == 0) {
+            const int64_t threads = (n + Q - 1) / Q;
+            const int64_t grid = (threads + THREADS - 1) / THREADS;
+            k_soa<SOLVER, T, THREADS, true><<<(unsigned)grid, THREADS, 0, st>>>(
+                src, tar, M, rp, H, degen, n, ld, normalize);
+        } else {
+            const int64_t grid = (n + THREADS - 1) / THREADS;
+            k_soa<SOLVER, T, THREADS, false><<<(unsigned)grid, THREADS, 0, st>>>(
+                src, tar, M, rp, H, degen, n, ld, normalize);
+        }
+        return finish_launch();
+    }
+
+    int variant = g_variant.load();
+    if (variant == 0) variant = 2;
+    constexpr int BIG = sizeof(T) == 4 ? 256 : 128;
+    constexpr int SMALL = BIG / 2;
+    if (variant == 1) {
+        const int64_t grid = (n + BIG - 1) / BIG;
+        k_aos_direct<SOLVER, T, BIG><<<(unsigned)grid, BIG, 0, st>>>(src, tar, M, rp, H, degen, n,
+                                                                     normalize);
+        return finish_launch();
+    }
+    if (g_tile_small.load())
+        return launch_ring<SOLVER, T, SMALL>(src, tar, M, rp, H, degen, n, normalize, dev, st);
+    return launch_ring<SOLVER, T, BIG>(src, tar, M, rp, H, degen, n, normalize, dev, st);
+}
+
+template <typename T>
+int launch_synth_quads(T* src, T* tar, int64_t begin, int64_t count, uint64_t seed, int dist,
+                       int layout, int64_t ld, void* stream)
+{
+    if (count < 0 || begin < 0 || src == nullptr || tar == nullptr) return SKS_ERR_INVALID_ARG;
+    if (dist < 0 || dist > 2 || (layout != SKS_LAYOUT_AOS && layout != SKS_LAYOUT_SOA))
+        return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (count == 0) return SKS_OK;
+    if (ld == 0) ld = count;
+    const int64_t grid = (count + 255) / 256;
+    k_synth_quads<T><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, tar, begin, count, seed_key(seed), dist, layout, ld);
+    return finish_launch();
+}
+
+template <typename T>
+int launch_gather(const T* pool, uint32_t pool_size, const uint32_t* rand4, uint64_t seed, T* src,
+                  T* tar, int64_t n, int layout, int64_t ld, void* stream)
+{
+    if (n < 0 || pool == nullptr || pool_size == 0 || src == nullptr || tar == nullptr)
+        return SKS_ERR_INVALID_ARG;
+    if (layout != SKS_LAYOUT_AOS && layout != SKS_LAYOUT_SOA) return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n == 0) return SKS_OK;
+    if (ld == 0) ld = n;
+    const int64_t grid = (n + 255) / 256;
+    k_gather_samples<T><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pool, pool_size, rand4, seed_key(seed), src, tar, n, layout, ld);
+    return finish_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+int sks_cuda_abi_version(void) { return SKS_CUDA_ABI_VERSION; }
+
+const char* sks_cuda_error_string(int status)
+{
+    switch (status) {
+        case SKS_OK: return "success";
+        case SKS_ERR_INVALID_ARG: return "invalid argument";
+        case SKS_ERR_UNALIGNED: return "pointer not 16-byte aligned";
+        case SKS_ERR_NO_DEVICE: return "no CUDA device (libsks_cuda has no CPU fallback)";
+        default: break;
+    }
+    return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown error";
+}
+
+int sks_cuda_device_count(int* count)
+{
+    if (count == nullptr) return SKS_ERR_INVALID_ARG;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SKS_ERR_NO_DEVICE : (int)e;
+    }
+    return SKS_OK;
+}
+
+#define SKS_DEFINE_GENERAL(NAME, SOLVER, T)                                                     \
+    int NAME(const T* src, const T* tar, T* H, int64_t n, int layout, int64_t ld, int flags,    \
+             uint8_t* degenerate, void* stream)                                                 \
+    {                                                                                           \
+        return launch_stream<SOLVER, T>(src, tar, nullptr, RectParams<T>{}, H, n, layout, ld,   \
+                                        flags, degenerate, stream);                             \
+    }
+SKS_DEFINE_GENERAL(sks_cuda_aca_f32, SOLVER_ACA, float)
+SKS_DEFINE_GENERAL(sks_cuda_aca_f64, SOLVER_ACA, double)
+SKS_DEFINE_GENERAL(sks_cuda_sks_f32, SOLVER_SKS, float)
+SKS_DEFINE_GENERAL(sks_cuda_sks_f64, SOLVER_SKS, double)
+
+#define SKS_DEFINE_RECT(NAME, T)                                                                \
+    int NAME(const T* tar, const T* M, T mx, T my, T width, T ratio, T* H, int64_t n,           \
+             int layout, int64_t ld, int flags, uint8_t* degenerate, void* stream)              \
+    {                                                                                           \
+        return launch_stream<SOLVER_RECT, T>(nullptr, tar, M, RectParams<T>{mx, my, width, ratio}, \
+                                             H, n, layout, ld, flags, degenerate, stream);      \
+    }
+SKS_DEFINE_RECT(sks_cuda_aca_rect_f32, float)
+SKS_DEFINE_RECT(sks_cuda_aca_rect_f64, double)
+
+int sks_cuda_gather_samples_f32(const float* pool, uint32_t pool_size, const uint32_t* rand4,
+                                uint64_t seed, float* src, float* tar, int64_t n, int layout,
+                                int64_t ld, void* stream)
+{
+    return launch_gather<float>(pool, pool_size, rand4, seed, src, tar, n, layout, ld, stream);
+}
+int sks_cuda_gather_samples_f64(const double* pool, uint32_t pool_size, const uint32_t* rand4,
+                                uint64_t seed, double* src, double* tar, int64_t n, int layout,
+                                int64_t ld, void* stream)
+{
+    return launch_gather<double>(pool, pool_size, rand4, seed, src, tar, n, layout, ld, stream);
+}
+
+int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
+                            const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,
+                            uint32_t hyp_count, uint64_t seed, float thr2,
+                            unsigned long long* best_key, void* stream)
+{
+    if (corr == nullptr || best_key == nullptr || n_pairs < 0 || n_pts <= 0)
+        return SKS_ERR_INVALID_ARG;
+    if (n_pairs > 65535) return SKS_ERR_INVALID_ARG;   // grid.y; shard larger batches
+    if (samples != nullptr && (hyp_stride < hyp_begin + hyp_count || !aligned16(samples)))
+        return SKS_ERR_INVALID_ARG;
+    if (!aligned16(corr)) return SKS_ERR_UNALIGNED;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n_pairs == 0 || hyp_count == 0) return SKS_OK;
+    const int32_t tile_pts = n_pts < kRansacMaxTilePts ? n_pts : kRansacMaxTilePts;
+    const int smem = tile_pts * 16;
+    cudaError_t e = cudaFuncSetAttribute(k_ransac_aca, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    // chunk: enough hypotheses per CTA to amortise the tile load, enough CTAs
+    // to fill the machine several times over
+    const uint32_t round = kRansacThreads * kRansacHpt;
+    uint32_t chunk = round * 8;
+    while (chunk > round &&
+           (int64_t)((hyp_count + chunk - 1) / chunk) * n_pairs < (int64_t)dev.sms * 8)
+        chunk -= round;
+    const unsigned chunks = (hyp_count + chunk - 1) / chunk;
+    dim3 grid(chunks, (unsigned)n_pairs);
+    k_ransac_aca<<<grid, kRansacThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(corr), n_pts, tile_pts, samples, hyp_stride, hyp_begin,
+        hyp_count, chunk, seed_key(seed), thr2, best_key);
+    return finish_launch();
+}
+
+int sks_cuda_ransac_finalize_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
+                                 const uint32_t* samples, uint32_t hyp_stride, uint64_t seed,
+                                 float thr2, const unsigned long long* best_key, float* H_best,
+                                 uint32_t* inlier_count, uint8_t* inlier_mask, void* stream)
+{
+    if (corr == nullptr || best_key == nullptr || H_best == nullptr || n_pairs < 0 || n_pts <= 0)
+        return SKS_ERR_INVALID_ARG;
+    if (!aligned16(corr) || (samples && !aligned16(samples))) return SKS_ERR_UNALIGNED;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n_pairs == 0) return SKS_OK;
+    k_ransac_finalize<<<(unsigned)n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(corr), n_pts, samples, hyp_stride, seed_key(seed), thr2,
+        best_key, H_best, inlier_count, inlier_mask);
+    return finish_launch();
+}
+
+int sks_cuda_synth_quads_f32(float* src, float* tar, int64_t begin, int64_t count, uint64_t seed,
+                             int dist, int layout, int64_t ld, void* stream)
+{
+    return launch_synth_quads<float>(src, tar, begin, count, seed, dist, layout, ld, stream);
+}
+int sks_cuda_synth_quads_f64(double* src, double* tar, int64_t begin, int64_t count,
+                             uint64_t seed, int dist, int layout, int64_t ld, void* stream)
+{
+    return launch_synth_quads<double>(src, tar, begin, count, seed, dist, layout, ld, stream);
+}
+
+int sks_cuda_synth_corr_f32(float* corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
+                            uint64_t seed, int inlier_permille, float noise, void* stream)
+{
+    if (corr == nullptr || n_pairs < 0 || n_pts <= 0 || pair_begin < 0) return SKS_ERR_INVALID_ARG;
+    if (!aligned16(corr)) return SKS_ERR_UNALIGNED;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n_pairs == 0) return SKS_OK;
+    const int64_t total = n_pairs * (int64_t)n_pts;
+    k_synth_corr<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4*>(corr), pair_begin, n_pairs, n_pts, seed_key(seed),
+        inlier_permille, noise);
+    return finish_launch();
+}
+
+int sks_cuda_shard_range(int64_t n, int rank, int world, int64_t* begin, int64_t* count)
+{
+    if (n < 0 || world <= 0 || rank < 0 || rank >= world || begin == nullptr || count == nullptr)
+        return SKS_ERR_INVALID_ARG;
+    const int64_t base = n / world, rem = n % world;
+    *begin = base * rank + (rank < rem ? rank : rem);
+    *count = base + (rank < rem ? 1 : 0);
+    return SKS_OK;
+}
+
+int64_t sks_cuda_launch_count(void) { return g_launches.load(); }
+void sks_cuda_reset_launch_count(void) { g_launches.store(0); }
+
+int sks_cuda_set_variant(int variant)
+{
+    if (variant < 0 || variant > 2) return SKS_ERR_INVALID_ARG;
+    g_variant.store(variant);
+    return SKS_OK;
+}
+int sks_cuda_get_variant(void) { return g_variant.load(); }
+
+int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm)
+{
+    if (stages < 2 || stages > 16 || ctas_per_sm < 0) return SKS_ERR_INVALID_ARG;
+    g_tile_small.store(small_tile ? 1 : 0);
+    g_stages.store(stages);
+    g_ctas_per_sm.store(ctas_per_sm);
+    return SKS_OK;
+}
+
+}  // extern "C"

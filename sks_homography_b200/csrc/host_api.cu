@@ -1,0 +1,297 @@
+// Host-pointer entry points: the drop-in for the reference's C++ call sites,
+// which hold plain host arrays (CPU/main.cpp:47-58,87-114).  A batch is cut
+// into chunks that flow through a ring of device buffers on independent
+// streams, so the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy
+// of chunk c-1 overlap (the path is PCIe-bound: 100 B cross the bus per
+// homography against ~100 flops of work).  Pinned caller buffers are copied
+// directly; pageable ones are staged through an internal pinned ring with a
+// multi-threaded memcpy.  The layer sits strictly above the device-pointer
+// C ABI: it calls sks_cuda_* like any other client.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sks_cuda.h"
+
+namespace {
+
+constexpr int kRing = 3;
+constexpr int64_t kChunkBytesIn = 32ll << 20;   // per input array per chunk
+
+struct Slot {
+    void* d_in[3] = {nullptr, nullptr, nullptr};   // src, tar, M
+    void* d_out = nullptr;
+    void* p_in[3] = {nullptr, nullptr, nullptr};   // pinned staging (pageable callers)
+    void* p_out = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    int64_t pending_off = -1, pending_cnt = 0;     // chunk whose D2H is in flight
+};
+
+struct HostCtx {
+    int device = -1;
+    int64_t cap_in = 0, cap_out = 0;   // bytes per device buffer
+    bool staged_in = false, staged_out = false;
+    Slot slot[kRing];
+};
+
+std::mutex g_mu;
+std::vector<HostCtx*> g_ctx;
+
+#define CK(x)                                  \
+    do {                                       \
+        cudaError_t _e = (x);                  \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+void free_ctx(HostCtx* c)
+{
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    for (Slot& s : c->slot) {
+        for (int k = 0; k < 3; ++k) {
+            if (s.d_in[k]) cudaFree(s.d_in[k]);
+            if (s.p_in[k]) cudaFreeHost(s.p_in[k]);
+        }
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.p_out) cudaFreeHost(s.p_out);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    cudaSetDevice(prev);
+    delete c;
+}
+
+int get_ctx(int64_t need_in, int64_t need_out, bool stage_in, bool stage_out, HostCtx** out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SKS_ERR_NO_DEVICE : (int)e;
+    }
+    HostCtx* c = nullptr;
+    for (HostCtx* x : g_ctx)
+        if (x->device == dev) c = x;
+    if (c == nullptr) {
+        c = new HostCtx();
+        c->device = dev;
+        g_ctx.push_back(c);
+        for (Slot& s : c->slot) {
+            CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+    }
+    if (need_in > c->cap_in) {
+        for (Slot& s : c->slot)
+            for (int k = 0; k < 3; ++k) {
+                if (s.d_in[k]) CK(cudaFree(s.d_in[k]));
+                s.d_in[k] = nullptr;
+                CK(cudaMalloc(&s.d_in[k], (size_t)need_in));
+                if (s.p_in[k]) CK(cudaFreeHost(s.p_in[k]));
+                s.p_in[k] = nullptr;
+            }
+        c->cap_in = need_in;
+        c->staged_in = false;
+    }
+    if (need_out > c->cap_out) {
+        for (Slot& s : c->slot) {
+            if (s.d_out) CK(cudaFree(s.d_out));
+            s.d_out = nullptr;
+            CK(cudaMalloc(&s.d_out, (size_t)need_out));
+            if (s.p_out) CK(cudaFreeHost(s.p_out));
+            s.p_out = nullptr;
+        }
+        c->cap_out = need_out;
+        c->staged_out = false;
+    }
+    if (stage_in && !c->staged_in) {
+        for (Slot& s : c->slot)
+            for (int k = 0; k < 3; ++k)
+                CK(cudaHostAlloc(&s.p_in[k], (size_t)c->cap_in, cudaHostAllocDefault));
+        c->staged_in = true;
+    }
+    if (stage_out && !c->staged_out) {
+        for (Slot& s : c->slot)
+            CK(cudaHostAlloc(&s.p_out, (size_t)c->cap_out, cudaHostAllocDefault));
+        c->staged_out = true;
+    }
+    *out = c;
+    return SKS_OK;
+}
+
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void parallel_copy(void* dst, const void* src, size_t bytes)
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, hw), bytes / (4u << 20) + 1);
+    if (nt <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 63) & ~size_t(63);
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, lo + per);
+        if (lo < hi)
+            th.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// Generic pipeline.  in[k] (k < n_in) are host arrays of in_elems[k] elements
+// per quadruple; out is 9 elements per quadruple; `launch` enqueues the solver
+// for `cnt` quadruples on device buffers.
+template <typename T, typename Launch>
+int run_pipeline(const T* const* in, const int* in_elems, int n_in, T* out, int64_t n, Launch launch)
+{
+    if (n < 0 || out == nullptr) return SKS_ERR_INVALID_ARG;
+    for (int k = 0; k < n_in; ++k)
+        if (in[k] == nullptr) return SKS_ERR_INVALID_ARG;
+    if (n == 0) {
+        int cnt = 0;
+        return sks_cuda_device_count(&cnt);
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, kChunkBytesIn / (8 * (int64_t)sizeof(T))));
+    bool stage_in = false;
+    for (int k = 0; k < n_in; ++k) stage_in = stage_in || !is_pinned(in[k]);
+    const bool stage_out = !is_pinned(out);
+    HostCtx* c = nullptr;
+    if (int rc = get_ctx(chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T), stage_in,
+                         stage_out, &c))
+        return rc;
+
+    auto drain = [&](Slot& s) -> int {   // finish the chunk this slot last produced
+        if (s.pending_off < 0) return SKS_OK;
+        CK(cudaEventSynchronize(s.done));
+        if (stage_out)
+            parallel_copy(out + s.pending_off * 9, s.p_out, (size_t)s.pending_cnt * 9 * sizeof(T));
+        s.pending_off = -1;
+        return SKS_OK;
+    };
+
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    int rc = SKS_OK;
+    for (int64_t ci = 0; ci < n_chunks && rc == SKS_OK; ++ci) {
+        Slot& s = c->slot[ci % kRing];
+        if ((rc = drain(s)) != SKS_OK) break;
+        const int64_t off = ci * chunk, cnt = std::min(chunk, n - off);
+        for (int k = 0; k < n_in; ++k) {
+            const size_t bytes = (size_t)cnt * in_elems[k] * sizeof(T);
+            const T* hsrc = in[k] + off * in_elems[k];
+            if (stage_in) {
+                parallel_copy(s.p_in[k], hsrc, bytes);
+                hsrc = static_cast<const T*>(s.p_in[k]);
+            }
+            CK(cudaMemcpyAsync(s.d_in[k], hsrc, bytes, cudaMemcpyHostToDevice, s.stream));
+        }
+        rc = launch(s, cnt);
+        if (rc != SKS_OK) break;
+        T* hdst = stage_out ? static_cast<T*>(s.p_out) : out + off * 9;
+        CK(cudaMemcpyAsync(hdst, s.d_out, (size_t)cnt * 9 * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaEventRecord(s.done, s.stream));
+        s.pending_off = off;
+        s.pending_cnt = cnt;
+    }
+    for (Slot& s : c->slot) {
+        const int r2 = drain(s);
+        if (rc == SKS_OK) rc = r2;
+    }
+    return rc;
+}
+
+template <typename T, typename Fn>
+int host_general(Fn fn, const T* src, const T* tar, T* H, int64_t n, int flags)
+{
+    const T* in[2] = {src, tar};
+    const int elems[2] = {8, 8};
+    return run_pipeline<T>(in, elems, 2, H, n, [&](Slot& s, int64_t cnt) {
+        return fn(static_cast<const T*>(s.d_in[0]), static_cast<const T*>(s.d_in[1]),
+                  static_cast<T*>(s.d_out), cnt, SKS_LAYOUT_AOS, 0, flags, nullptr, s.stream);
+    });
+}
+
+template <typename T, typename Fn>
+int host_rect(Fn fn, const T* tar, const T* M, T mx, T my, T width, T ratio, T* H, int64_t n, int flags)
+{
+    const T* in[2] = {tar, M};
+    const int elems[2] = {8, 2};
+    return run_pipeline<T>(in, elems, M ? 2 : 1, H, n, [&](Slot& s, int64_t cnt) {
+        return fn(static_cast<const T*>(s.d_in[0]), M ? static_cast<const T*>(s.d_in[1]) : nullptr,
+                  mx, my, width, ratio, static_cast<T*>(s.d_out), cnt, SKS_LAYOUT_AOS, 0, flags,
+                  nullptr, s.stream);
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+int sks_host_aca_f32(const float* src, const float* tar, float* H, int64_t n, int flags)
+{
+    return host_general<float>(sks_cuda_aca_f32, src, tar, H, n, flags);
+}
+int sks_host_aca_f64(const double* src, const double* tar, double* H, int64_t n, int flags)
+{
+    return host_general<double>(sks_cuda_aca_f64, src, tar, H, n, flags);
+}
+int sks_host_sks_f32(const float* src, const float* tar, float* H, int64_t n, int flags)
+{
+    return host_general<float>(sks_cuda_sks_f32, src, tar, H, n, flags);
+}
+int sks_host_sks_f64(const double* src, const double* tar, double* H, int64_t n, int flags)
+{
+    return host_general<double>(sks_cuda_sks_f64, src, tar, H, n, flags);
+}
+int sks_host_aca_rect_f32(const float* tar, const float* M, float mx, float my, float width,
+                          float ratio, float* H, int64_t n, int flags)
+{
+    return host_rect<float>(sks_cuda_aca_rect_f32, tar, M, mx, my, width, ratio, H, n, flags);
+}
+int sks_host_aca_rect_f64(const double* tar, const double* M, double mx, double my, double width,
+                          double ratio, double* H, int64_t n, int flags)
+{
+    return host_rect<double>(sks_cuda_aca_rect_f64, tar, M, mx, my, width, ratio, H, n, flags);
+}
+
+int sks_host_alloc_pinned(void** ptr, int64_t bytes)
+{
+    if (ptr == nullptr || bytes < 0) return SKS_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SKS_ERR_NO_DEVICE : (int)e;
+    }
+    return SKS_OK;
+}
+int sks_host_free_pinned(void* ptr)
+{
+    cudaError_t e = cudaFreeHost(ptr);
+    return e == cudaSuccess ? SKS_OK : (int)e;
+}
+
+int sks_cuda_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (HostCtx* c : g_ctx) free_ctx(c);
+    g_ctx.clear();
+    return SKS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+// Fused ACA-RANSAC: hypothesis generation, scoring and best-model selection in
+// one kernel; no per-hypothesis homography ever touches HBM.
+//
+// Nothing like this exists in the reference; the sampler follows its precedent
+// (r % size with repeats allowed, GPU.cu:52-78) and every hypothesis is the
+// bit-exact fp32 ACA (MOD/ACA_SKS.cpp:24-102).  The scoring rule is this
+// project's definition and is mirrored operation for operation by
+// oracle_ransac_count_f32 (oracle/sks_oracle.c) so inlier counts are bit-exact:
+//     u = fma(h0,x,fma(h1,y,h2));  v = fma(h3,x,fma(h4,y,h5));
+//     w = fma(h6,x,fma(h7,y,h8));
+//     du = fma(X,w,-u); dv = fma(Y,w,-v); e = fma(dv,dv,du*du)
+//     inlier <=> e < (thr2*w)*w          (division-free forward transfer error)
+//
+// Mapping: a CTA owns one image pair and a contiguous chunk of hypothesis ids.
+// The pair's correspondences (x,y,X,Y) are pulled into shared memory once by
+// the bulk-copy engine (64 KiB for 4096 points); every thread then carries HPT
+// hypotheses in registers and walks the tile with warp-uniform (broadcast)
+// 16-byte shared loads, so the inner loop is pure FP32 pipe work.  The best
+// (count, lowest id) is reduced with warp shuffles, then one 64-bit atomicMax
+// per CTA.  Bound: FP32 pipe (~12 FP32 + 2 integer instructions per
+// hypothesis x point), not HBM.
+#pragma once
+#include <cstdint>
+
+#include "ptx.cuh"
+#include "solvers.cuh"
+#include "synth.cuh"
+
+namespace sksb {
+
+constexpr int kRansacThreads = 256;
+constexpr int kRansacHpt = 2;              // hypotheses per thread per round
+constexpr int kRansacMaxTilePts = 8192;    // 128 KiB of shared memory at most
+
+__device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, uint32_t hyp,
+                                              const uint32_t* __restrict__ samples,
+                                              uint32_t hyp_stride, uint32_t n_pts, uint32_t (&idx)[4])
+{
+    if (samples != nullptr) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(samples) +
+                              ((size_t)pair * hyp_stride + hyp));
+        idx[0] = v.x; idx[1] = v.y; idx[2] = v.z; idx[3] = v.w;
+    } else {
+        const uint64_t ctr = ((uint64_t)pair << 32) | (uint64_t)hyp;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            idx[k] = (uint32_t)(rng_u64(key, ctr, k) >> 32) % n_pts;
+    }
+}
+
+__device__ __forceinline__ void ransac_hypothesis(const float4* __restrict__ corr_pair,
+                                                  const uint32_t (&idx)[4], float (&h)[9])
+{
+    float s[8], t[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 c = __ldg(corr_pair + idx[k]);
+        s[2 * k] = c.x; s[2 * k + 1] = c.y;
+        t[2 * k] = c.z; t[2 * k + 1] = c.w;
+    }
+    aca_solve<float>(s, t, h, true);
+}
+
+__device__ __forceinline__ bool ransac_inlier(const float (&h)[9], const float4 c, float thr2)
+{
+    const float u = __fmaf_rn(h[0], c.x, __fmaf_rn(h[1], c.y, h[2]));
+    const float v = __fmaf_rn(h[3], c.x, __fmaf_rn(h[4], c.y, h[5]));
+    const float w = __fmaf_rn(h[6], c.x, __fmaf_rn(h[7], c.y, h[8]));
+    const float du = __fmaf_rn(c.z, w, -u);
+    const float dv = __fmaf_rn(c.w, w, -v);
+    const float e = __fmaf_rn(dv, dv, __fmul_rn(du, du));
+    const float lim = __fmul_rn(__fmul_rn(thr2, w), w);
+    return e < lim;
+}
+
+__device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_t hyp)
+{
+    return ((unsigned long long)count << 32) | (unsigned long long)(0xFFFFFFFFu - hyp);
+}
+
+// grid = (chunks_per_pair, n_pairs); each CTA scores hypothesis ids
+// [hyp_begin + chunk*chunk_size, +chunk_size) ∩ [hyp_begin, hyp_begin+hyp_count)
+__global__ void __launch_bounds__(kRansacThreads)
+k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
+             const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
+             uint32_t hyp_count, uint32_t chunk_size, uint64_t key, float thr2,
+             unsigned long long* __restrict__ best_key)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* tile = reinterpret_cast<float4*>(smem);
+    __shared__ uint64_t bar;
+    __shared__ unsigned long long warp_best[kRansacThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t pair = blockIdx.y;
+    const float4* corr_pair = corr + (size_t)pair * n_pts;
+    const uint32_t c_lo = blockIdx.x * chunk_size;
+    if (c_lo >= hyp_count)
+        return;
+    const uint32_t c_hi = (hyp_count - c_lo < chunk_size) ? hyp_count : c_lo + chunk_size;
+    const int n_tiles = (n_pts + tile_pts - 1) / tile_pts;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    auto load_tile = [&](int tl) {   // thread 0: one bulk copy per tile
+        const int lo = tl * tile_pts;
+        const int cnt = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
+        mbar_arrive_expect_tx(&bar, (uint32_t)cnt * 16u);
+        bulk_g2s(tile, corr_pair + lo, (uint32_t)cnt * 16u, &bar);
+    };
+    if (tid == 0)
+        load_tile(0);
+    bool resident = false;   // single tile stays in shared memory for all rounds
+
+    unsigned long long best = 0ull;
+    for (uint32_t base = c_lo; base < c_hi; base += kRansacThreads * kRansacHpt) {
+        float h[kRansacHpt][9];
+        uint32_t cnt[kRansacHpt], hyp[kRansacHpt];
+        bool live[kRansacHpt];
+#pragma unroll
+        for (int j = 0; j < kRansacHpt; ++j) {
+            const uint32_t local = base + (uint32_t)j * kRansacThreads + tid;
+            live[j] = local < c_hi;
+            hyp[j] = hyp_begin + (live[j] ? local : c_lo);
+            uint32_t idx[4];
+            ransac_sample(key, pair, hyp[j], samples, hyp_stride, (uint32_t)n_pts, idx);
+            ransac_hypothesis(corr_pair, idx, h[j]);
+            cnt[j] = 0;
+        }
+        for (int tl = 0; tl < n_tiles; ++tl) {
+            if (!resident) {
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+                resident = (n_tiles == 1);
+            }
+            const int lo = tl * tile_pts;
+            const int np = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
+            int i = 0;
+            for (; i + 4 <= np; i += 4) {
+                float4 c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    c[k] = tile[i + k];   // warp-uniform address: broadcast
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int j = 0; j < kRansacHpt; ++j)
+                        cnt[j] += ransac_inlier(h[j], c[k], thr2) ? 1u : 0u;
+            }
+            for (; i < np; ++i) {
+                const float4 c = tile[i];
+#pragma unroll
+                for (int j = 0; j < kRansacHpt; ++j)
+                    cnt[j] += ransac_inlier(h[j], c, thr2) ? 1u : 0u;
+            }
+            if (n_tiles > 1) {   // stream the next tile (wraps for the next round)
+                __syncthreads();
+                const bool more = (tl + 1 < n_tiles) ||
+                                  (base + kRansacThreads * kRansacHpt < c_hi);
+                if (tid == 0 && more)
+                    load_tile((tl + 1) % n_tiles);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kRansacHpt; ++j)
+            if (live[j]) {
+                const unsigned long long k = ransac_key(cnt[j], hyp[j]);
+                best = k > best ? k : best;
+            }
+    }
+    // CTA-wide max: shuffles inside the warp, shared memory across warps
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+        best = o > best ? o : best;
+    }
+    if ((tid & 31) == 0)
+        warp_best[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int wv = 1; wv < kRansacThreads / 32; ++wv)
+            best = warp_best[wv] > best ? warp_best[wv] : best;
+        atomicMax(best_key + pair, best);
+    }
+}
+
+// One CTA per pair: rebuild the winning hypothesis from its id and emit the
+// model, its inlier count and (optionally) the inlier mask.
+__global__ void __launch_bounds__(256)
+k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
+                  const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint64_t key,
+                  float thr2, const unsigned long long* __restrict__ best_key,
+                  float* __restrict__ H_best, uint32_t* __restrict__ inlier_count,
+                  uint8_t* __restrict__ inlier_mask)
+{
+    __shared__ float hs[9];
+    __shared__ uint32_t total;
+    const int64_t pair = blockIdx.x;
+    const float4* corr_pair = corr + (size_t)pair * n_pts;
+    if (threadIdx.x == 0) {
+        const uint32_t hyp = 0xFFFFFFFFu - (uint32_t)(best_key[pair] & 0xFFFFFFFFull);
+        uint32_t idx[4];
+        float h[9];
+        ransac_sample(key, pair, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
+        ransac_hypothesis(corr_pair, idx, h);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            hs[k] = h[k];
+            H_best[pair * 9 + k] = h[k];
+        }
+        total = 0;
+    }
+    __syncthreads();
+    float h[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        h[k] = hs[k];
+    uint32_t mine = 0;
+    for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
+        const bool in = ransac_inlier(h, __ldg(corr_pair + i), thr2);
+        mine += in ? 1u : 0u;
+        if (inlier_mask != nullptr)
+            inlier_mask[(size_t)pair * n_pts + i] = in ? 1 : 0;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0)
+        atomicAdd(&total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && inlier_count != nullptr)
+        inlier_count[pair] = total;
+}
+
+}  // namespace sksb

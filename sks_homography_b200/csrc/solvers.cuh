@@ -1,0 +1,236 @@
+// Per-quadruple closed-form solvers (device functions).  One thread solves one
+// correspondence quadruple entirely in registers: 16 (or 8) coordinates in,
+// 9 homography entries out.  The operation ORDER is the reference's, because
+// parity is bit-exact (see strict.cuh); the code is organised around the
+// geometry (2-D cross products, planar rotations, row products) rather than
+// the reference's flat scalar listing.
+//
+//   aca_solve      <- sks::runKernel_ACA[_double]   MOD/ACA_SKS.cpp:24-102, :104-179
+//                     cal_Homo_ACA (no normalise)   GPU.cu:81-151
+//   sks_solve      <- sks::runKernel_SKS[_double]   MOD/ACA_SKS.cpp:189-303, :305-418
+//                     cal_Homo_SKS (no normalise)   GPU.cu:153-240
+//   aca_rect_solve <- ACA_rect                      ML/ACA_rect.m:25-36
+//                     TensorACA_rect                PY.py:296-302
+#pragma once
+#include "strict.cuh"
+
+namespace sksb {
+
+template <typename T>
+struct Vec2 {
+    Strict<T> x, y;
+};
+
+// a.x*b.y - a.y*b.x, both products rounded before the subtraction
+template <typename T>
+__device__ __forceinline__ Strict<T> cross(Vec2<T> a, Vec2<T> b)
+{
+    return a.x * b.y - a.y * b.x;
+}
+
+// h[0..7] *= 1/h[8]; h[8] = 1   (MOD/ACA_SKS.cpp:94-98): one IEEE division,
+// eight multiplies, h33 forced to one even when the reciprocal is not finite.
+template <typename T>
+__device__ __forceinline__ void scale_by_h33(T (&h)[9])
+{
+    const Strict<T> inv = Strict<T>(T(1)) / Strict<T>(h[8]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        h[k] = (Strict<T>(h[k]) * inv).v;
+    h[8] = T(1);
+}
+
+// Degeneracy flag, SURVEY.md A.3: the reference signals a singular quadruple
+// only through non-finite output.
+template <typename T>
+__device__ __forceinline__ bool is_degenerate(const T (&h)[9], bool normalized)
+{
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        ok = ok && finite_val<T>(h[k]);
+    if (!normalized)
+        ok = ok && finite_val<T>(h[8]) && h[8] != T(0);
+    return !ok;
+}
+
+// ---------------------------------------------------------------------- ACA
+// Affine frame of one plane: u = N-M, v = P-M, q = Q-M; f = u x v is twice the
+// triangle area and g = (q x v, u x q) the affine coordinates of Q scaled by f.
+template <typename T>
+struct AffineFrame {
+    Vec2<T> u, v;
+    Strict<T> f, gx, gy;
+};
+
+template <typename T>
+__device__ __forceinline__ AffineFrame<T> affine_frame(const T (&p)[8])
+{
+    using S = Strict<T>;
+    AffineFrame<T> F;
+    F.u = { S(p[2]) - S(p[0]), S(p[3]) - S(p[1]) };
+    F.v = { S(p[4]) - S(p[0]), S(p[5]) - S(p[1]) };
+    const Vec2<T> q = { S(p[6]) - S(p[0]), S(p[7]) - S(p[1]) };
+    F.f = cross(F.u, F.v);
+    F.gx = cross(q, F.v);
+    F.gy = cross(F.u, q);
+    return F;
+}
+
+template <typename T>
+__device__ __forceinline__ void aca_solve(const T (&s)[8], const T (&t)[8], T (&h)[9],
+                                          bool normalize)
+{
+    using S = Strict<T>;
+    const AffineFrame<T> A = affine_frame<T>(s);   // source plane
+    const AffineFrame<T> B = affine_frame<T>(t);   // target plane
+
+    // core transformation: diag(c1,c2,c3) with last row (c1-c3, c2-c3, c3)
+    const S k1 = (A.f - A.gx) - A.gy;
+    const S c1 = (A.gy * B.gx) * k1;
+    const S c2 = (A.gx * B.gy) * k1;
+    const S c3 = (A.gx * A.gy) * ((B.f - B.gx) - B.gy);
+
+    // rows (a_r, b_r, c_r) of H_A2^-1 * H_C
+    const S mx = S(t[0]) * c3, my = S(t[1]) * c3;
+    const S a[3] = { S(t[2]) * c1 - mx, S(t[3]) * c1 - my, c1 - c3 };
+    const S b[3] = { S(t[4]) * c2 - mx, S(t[5]) * c2 - my, c2 - c3 };
+    const S c[3] = { mx, my, c3 };
+
+    // times H_A1 = [[v.y,-v.x,0],[-u.y,u.x,0],[0,0,f]] * T(-M1): the third
+    // column re-uses the first two
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const S e0 = a[r] * A.v.y - b[r] * A.u.y;
+        const S e1 = b[r] * A.u.x - a[r] * A.v.x;
+        h[3 * r + 0] = e0.v;
+        h[3 * r + 1] = e1.v;
+        h[3 * r + 2] = ((c[r] * A.f - e0 * S(s[0])) - e1 * S(s[1])).v;
+    }
+    if (normalize)
+        scale_by_h33<T>(h);
+}
+
+// ---------------------------------------------------------------------- SKS
+// Similarity frame of the anchor pair (M,N): midpoint o, half vector w with
+// its y component flipped, squared length f.  MOD/ACA_SKS.cpp:192-206.
+template <typename T>
+struct SimFrame {
+    Strict<T> ox, oy, wx, wy, f;
+};
+
+template <typename T>
+__device__ __forceinline__ SimFrame<T> sim_frame(const T (&p)[8])
+{
+    using S = Strict<T>;
+    SimFrame<T> F;
+    F.ox = S(T(0.5)) * (S(p[0]) + S(p[2]));
+    F.oy = S(T(0.5)) * (S(p[1]) + S(p[3]));
+    F.wx = F.ox - S(p[0]);
+    F.wy = S(p[1]) - F.oy;
+    F.f = F.wx * F.wx + F.wy * F.wy;
+    return F;
+}
+
+// P and Q carried through similarity, elementary and translation steps
+// (MOD/ACA_SKS.cpp:217-232 source plane, :238-253 target plane).
+template <typename T>
+struct KernelPts {
+    Strict<T> px, py, qx, qy, qf;
+};
+
+template <typename T>
+__device__ __forceinline__ KernelPts<T> carry_points(const SimFrame<T>& F, const T (&p)[8])
+{
+    using S = Strict<T>;
+    KernelPts<T> K;
+    const S ax = S(p[4]) - F.ox, ay = S(p[5]) - F.oy;
+    const S p3x = F.wx * ax - F.wy * ay;
+    const S p3y = F.wy * ax + F.wx * ay;
+    const S inv = S(T(1)) / p3y;
+    K.px = inv * p3x;
+    K.py = inv * F.f;
+    const S bx = S(p[6]) - F.ox, by = S(p[7]) - F.oy;
+    const S q3x = F.wx * bx - F.wy * by;
+    const S q3y = F.wy * bx + F.wx * by;
+    K.qx = p3y * q3x - p3x * q3y;
+    K.qy = (p3y - q3y) * F.f;
+    K.qf = p3y * q3y;
+    return K;
+}
+
+template <typename T>
+__device__ __forceinline__ void sks_solve(const T (&s)[8], const T (&t)[8], T (&h)[9],
+                                          bool normalize)
+{
+    using S = Strict<T>;
+    const SimFrame<T> F1 = sim_frame<T>(s);
+    const SimFrame<T> F2 = sim_frame<T>(t);
+    const KernelPts<T> A = carry_points<T>(F1, s);
+    const KernelPts<T> B = carry_points<T>(F2, t);
+
+    // hyperbolic similarity parameters (MOD/ACA_SKS.cpp:263-270)
+    const S n1 = A.qx * B.qx - A.qy * B.qy;
+    const S n2 = A.qx * B.qy - A.qy * B.qx;
+    S d = A.qx * A.qx - A.qy * A.qy;
+    d = A.qf / (d * B.qf);
+    const S aK = n1 * d, bK = n2 * d;
+    const S uK = (B.px - aK * A.px) - bK * A.py;
+    const S vK = (B.py - aK * A.py) - bK * A.px;
+
+    // H_L = H_S2^-1 * H_K (:276-278)
+    const S L[9] = {
+        bK * F2.ox + aK * F2.wx, (F2.wy + F2.ox * vK) + uK * F2.wx, aK * F2.ox + bK * F2.wx,
+        bK * F2.oy - aK * F2.wy, (F2.wx + F2.oy * vK) - uK * F2.wy, aK * F2.oy - bK * F2.wy,
+        bK, vK, aK
+    };
+    // last column of H_S1 (:281-282)
+    const S s13 = F1.wy * F1.oy - F1.wx * F1.ox;
+    const S s23 = (-F1.wy) * F1.ox - F1.wx * F1.oy;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const S a = L[3 * r], b = L[3 * r + 1], c = L[3 * r + 2];
+        h[3 * r + 0] = (a * F1.wx + b * F1.wy).v;
+        h[3 * r + 1] = (b * F1.wx - a * F1.wy).v;
+        h[3 * r + 2] = ((c * F1.f + a * s13) + b * s23).v;
+    }
+    if (normalize)
+        scale_by_h33<T>(h);
+}
+
+// ----------------------------------------------------------------- ACA-rect
+// Source = axis-aligned rectangle, top-left (mx,my), width, ratio = w/h.
+template <typename T>
+__device__ __forceinline__ void aca_rect_solve(const T (&t)[8], T mx_, T my_, T width_,
+                                               T ratio_, T (&h)[9], bool normalize)
+{
+    using S = Strict<T>;
+    const S mx(mx_), my(my_), width(width_), ratio(ratio_);
+    const S dx1 = S(t[2]) - S(t[0]), dx2 = S(t[4]) - S(t[0]), dx3 = S(t[6]) - S(t[0]);
+    const S dy1 = S(t[3]) - S(t[1]), dy2 = S(t[5]) - S(t[1]), dy3 = S(t[7]) - S(t[1]);
+    // c = cross(d_y, d_x), y row first (ML/ACA_rect.m:26)
+    const S c1 = dy2 * dx3 - dy3 * dx2;
+    const S c2 = dy3 * dx1 - dy1 * dx3;
+    const S c3 = dy1 * dx2 - dy2 * dx1;
+    const S sc = (c1 + c2) + c3;
+    const S one(T(1));
+    const S b[3] = { sc * S(t[0]), sc * S(t[1]), sc * one };
+    const S n[3] = { S(t[2]), S(t[3]), one };
+    const S p[3] = { S(t[4]), S(t[5]), one };
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const S e0 = n[r] * c1 - b[r];
+        const S e1 = ratio * (p[r] * c2 - b[r]);
+        h[3 * r + 0] = e0.v;
+        h[3 * r + 1] = e1.v;
+        h[3 * r + 2] = ((width * b[r] - mx * e0) - my * e1).v;
+    }
+    if (normalize) {   // H ./ H(3,3): element-wise division (ML/ACA_rect.m:36)
+        const S den(h[8]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            h[k] = (S(h[k]) / den).v;
+    }
+}
+
+}  // namespace sksb

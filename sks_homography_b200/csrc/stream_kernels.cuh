@@ -1,0 +1,386 @@
+// Streaming solver kernels: one thread per correspondence quadruple, HBM-bound
+// (arithmetic intensity ~1 flop/B, >10x below the B200 ridge, so no tensor
+// cores: there is no contraction to feed them).  Three kernels per
+// (solver, precision):
+//
+//   k_aos_ring    persistent CTAs; the AoS input tiles are pulled into a
+//                 multi-stage shared-memory ring by the bulk async-copy (TMA)
+//                 engine (cp.async.bulk + mbarrier), each thread reads its own
+//                 32/64-byte quadruple with conflict-free swizzled 16-byte
+//                 shared loads, and the 9-word results are transposed through
+//                 shared memory and leave as one bulk shared->global copy per
+//                 tile.  No register-staged global traffic at all.
+//   k_aos_direct  one tile per CTA; per-thread 16-byte read-only loads, results
+//                 transposed through shared memory into coalesced 16-byte
+//                 stores.  Simple comparison point / fallback for odd sizes.
+//   k_soa         the reference GPU layout (GPU.cu:87-95,141-149): 16-byte
+//                 coalesced loads of 4 (fp32) / 2 (fp64) consecutive quadruples
+//                 per thread per coordinate plane, streaming cache hints.
+#pragma once
+#include <cstdint>
+
+#include "ptx.cuh"
+#include "solvers.cuh"
+
+namespace sksb {
+
+enum { SOLVER_ACA = 0, SOLVER_SKS = 1, SOLVER_RECT = 2 };
+
+template <typename T>
+struct RectParams {
+    T mx, my, width, ratio;
+};
+
+template <int SOLVER, typename T>
+__device__ __forceinline__ void solve_quad(const T (&s)[8], const T (&t)[8], T mx, T my,
+                                           const RectParams<T>& rp, T (&h)[9], bool normalize)
+{
+    if constexpr (SOLVER == SOLVER_ACA)
+        aca_solve<T>(s, t, h, normalize);
+    else if constexpr (SOLVER == SOLVER_SKS)
+        sks_solve<T>(s, t, h, normalize);
+    else
+        aca_rect_solve<T>(t, mx, my, rp.width, rp.ratio, h, normalize);
+}
+
+// ---- 16-byte chunk <-> scalars ---------------------------------------------
+template <typename T>
+struct ChunkTraits;
+template <>
+struct ChunkTraits<float> {
+    static constexpr int EPC = 4;   // elements per 16-byte chunk
+    static __device__ __forceinline__ float get(const Chunk16& c, int e) { return __uint_as_float(c.w[e]); }
+    static __device__ __forceinline__ void set(Chunk16& c, int e, float v) { c.w[e] = __float_as_uint(v); }
+};
+template <>
+struct ChunkTraits<double> {
+    static constexpr int EPC = 2;
+    static __device__ __forceinline__ double get(const Chunk16& c, int e)
+    {
+        return __hiloint2double((int)c.w[2 * e + 1], (int)c.w[2 * e]);
+    }
+    static __device__ __forceinline__ void set(Chunk16& c, int e, double v)
+    {
+        c.w[2 * e] = (uint32_t)__double2loint(v);
+        c.w[2 * e + 1] = (uint32_t)__double2hiint(v);
+    }
+};
+
+__device__ __forceinline__ Chunk16 pick(bool second, const Chunk16& a, const Chunk16& b)
+{
+    Chunk16 r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        r.w[k] = second ? b.w[k] : a.w[k];
+    return r;
+}
+
+// One quadruple (8 scalars) straight from global memory, 16 bytes at a time.
+template <typename T>
+__device__ __forceinline__ void load_quad_global(const T* p, T (&v)[8])
+{
+    constexpr int EPC = ChunkTraits<T>::EPC, NC = 8 / EPC;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const Chunk16 c = ldg_nc(p + j * EPC);
+#pragma unroll
+        for (int e = 0; e < EPC; ++e)
+            v[j * EPC + e] = ChunkTraits<T>::get(c, e);
+    }
+}
+
+// One quadruple from an AoS shared-memory tile.  Thread `tid` owns bytes
+// [tid*8*sizeof(T), +8*sizeof(T)); a plain 16-byte read at that stride is a
+// 2-way (fp32) / 4-way (fp64) bank conflict, so each quarter-warp reads its
+// chunks in a rotated order that covers all 32 banks exactly once, and the
+// rotation is undone in registers with selects.
+template <typename T>
+__device__ __forceinline__ void load_quad_smem(const unsigned char* tile, int tid, T (&v)[8])
+{
+    constexpr int EPC = ChunkTraits<T>::EPC, NC = 8 / EPC;
+    const unsigned char* mine = tile + (size_t)tid * (8 * sizeof(T));
+    Chunk16 d[NC];
+    if constexpr (NC == 2) {
+        const int r = (tid >> 2) & 1;
+        const Chunk16 c0 = lds16(mine + 16 * r);
+        const Chunk16 c1 = lds16(mine + 16 * (r ^ 1));
+        d[0] = pick(r, c0, c1);
+        d[1] = pick(r, c1, c0);
+    } else {
+        const int r = (tid >> 1) & 3;
+        Chunk16 c[4], e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            c[j] = lds16(mine + 16 * ((j + r) & 3));   // c[j] = chunk[(j+r)&3]
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            e[j] = pick(r & 1, c[j], c[(j + 3) & 3]);  // e[j] = chunk[(j+(r&2))&3]
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            d[j] = pick(r & 2, e[j], e[(j + 2) & 3]);  // d[j] = chunk[j]
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int e = 0; e < EPC; ++e)
+            v[j * EPC + e] = ChunkTraits<T>::get(d[j], e);
+}
+
+// per-quadruple rectangle corner (AoS M[i*2+k])
+template <typename T>
+__device__ __forceinline__ void load_corner_aos(const T* M, int64_t i, T& mx, T& my)
+{
+    if constexpr (sizeof(T) == 4) {
+        const float2 m = __ldg(reinterpret_cast<const float2*>(M) + i);
+        mx = m.x;
+        my = m.y;
+    } else {
+        const double2 m = __ldg(reinterpret_cast<const double2*>(M) + i);
+        mx = m.x;
+        my = m.y;
+    }
+}
+
+// ------------------------------------------------------------ k_aos_direct
+template <int SOLVER, typename T, int TILE>
+__global__ void __launch_bounds__(TILE)
+k_aos_direct(const T* __restrict__ src, const T* __restrict__ tar, const T* __restrict__ M,
+             RectParams<T> rp, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n,
+             bool normalize)
+{
+    __shared__ __align__(16) T stage[TILE * 9];
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.x * TILE;
+    const int64_t i = q0 + tid;
+    const int cnt = (int)((n - q0) < (int64_t)TILE ? (n - q0) : (int64_t)TILE);
+    if (tid < cnt) {
+        T s[8], t[8], h[9];
+        T mx = rp.mx, my = rp.my;
+        if constexpr (SOLVER != SOLVER_RECT)
+            load_quad_global<T>(src + i * 8, s);
+        load_quad_global<T>(tar + i * 8, t);
+        if constexpr (SOLVER == SOLVER_RECT)
+            if (M != nullptr)
+                load_corner_aos<T>(M, i, mx, my);
+        solve_quad<SOLVER, T>(s, t, mx, my, rp, h, normalize);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            stage[tid * 9 + k] = h[k];   // stride 9 words: conflict-free
+        if (degen != nullptr)
+            degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
+    }
+    __syncthreads();
+    // the tile's results are contiguous in H: cnt*9 elements from H + q0*9
+    const int total = cnt * 9;
+    constexpr int EPC = ChunkTraits<T>::EPC;
+    const int nchunk = total / EPC;
+    T* dst = H + q0 * 9;
+    for (int c = tid; c < nchunk; c += TILE)
+        stg_stream(dst + c * EPC, lds16(stage + c * EPC));
+    for (int e = nchunk * EPC + tid; e < total; e += TILE)
+        dst[e] = stage[e];
+}
+
+// -------------------------------------------------------------- k_aos_ring
+template <int SOLVER, typename T, int TILE>
+struct RingLayout {
+    static constexpr int ARR_BYTES = TILE * 8 * (int)sizeof(T);
+    static constexpr int NARR = (SOLVER == SOLVER_RECT) ? 1 : 2;
+    static constexpr int STAGE_BYTES = ARR_BYTES * NARR;
+    static constexpr int OUT_BYTES = TILE * 9 * (int)sizeof(T);
+    static __host__ __device__ constexpr int smem_bytes(int stages)
+    {
+        return stages * STAGE_BYTES + 2 * OUT_BYTES + stages * 8;
+    }
+};
+
+template <int SOLVER, typename T, int TILE>
+__global__ void __launch_bounds__(TILE)
+k_aos_ring(const T* __restrict__ src, const T* __restrict__ tar, const T* __restrict__ M,
+           RectParams<T> rp, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n,
+           int stages, bool normalize)
+{
+    using L = RingLayout<SOLVER, T, TILE>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* ring = smem;
+    T* out_base = reinterpret_cast<T*>(smem + stages * L::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * L::STAGE_BYTES + 2 * L::OUT_BYTES);
+
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+
+    // producer side (thread 0): arm the stage's barrier with the byte count and
+    // hand both AoS tiles to the bulk-copy engine
+    auto issue = [&](int64_t it, int s) {
+        const int64_t q0 = (first + it * stride) * TILE;
+        const int64_t left = n - q0;
+        const uint32_t cnt = (uint32_t)(left < (int64_t)TILE ? left : (int64_t)TILE);
+        const uint32_t bytes = cnt * 8u * (uint32_t)sizeof(T);
+        unsigned char* dst = ring + s * L::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], bytes * L::NARR);
+        if constexpr (SOLVER != SOLVER_RECT) {
+            bulk_g2s(dst, src + q0 * 8, bytes, &full[s]);
+            bulk_g2s(dst + L::ARR_BYTES, tar + q0 * 8, bytes, &full[s]);
+        } else {
+            bulk_g2s(dst, tar + q0 * 8, bytes, &full[s]);
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s)
+            mbar_init(&full[s], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < stages && s < my_tiles; ++s)
+            issue(s, s);
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t q0 = (first + it * stride) * TILE;
+        const int64_t left = n - q0;
+        const int cnt = (int)(left < (int64_t)TILE ? left : (int64_t)TILE);
+        const bool active = tid < cnt;
+        const int64_t i = q0 + tid;
+
+        T mx = rp.mx, my = rp.my;
+        if constexpr (SOLVER == SOLVER_RECT)
+            if (M != nullptr && active)
+                load_corner_aos<T>(M, i, mx, my);
+
+        mbar_wait(&full[s], parity);   // this stage's bytes have landed
+        T sv[8], tv[8];
+        if (active) {
+            const unsigned char* st = ring + s * L::STAGE_BYTES;
+            if constexpr (SOLVER != SOLVER_RECT) {
+                load_quad_smem<T>(st, tid, sv);
+                load_quad_smem<T>(st + L::ARR_BYTES, tid, tv);
+            } else {
+                load_quad_smem<T>(st, tid, tv);
+            }
+        }
+        // the output buffer about to be overwritten was handed to the copy
+        // engine two tiles ago; make sure it has been read out
+        if (tid == 0)
+            bulk_wait_read<1>();
+        __syncthreads();   // stage s fully consumed, out[it&1] free
+        if (tid == 0 && it + stages < my_tiles)
+            issue(it + stages, s);
+
+        T* out = out_base + (size_t)(it & 1) * (TILE * 9);
+        if (active) {
+            T h[9];
+            solve_quad<SOLVER, T>(sv, tv, mx, my, rp, h, normalize);
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                out[tid * 9 + k] = h[k];
+            if (degen != nullptr)
+                degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
+        }
+        fence_async_smem();
+        __syncthreads();
+        const uint32_t out_bytes = (uint32_t)cnt * 9u * (uint32_t)sizeof(T);
+        if ((out_bytes & 15u) == 0) {
+            if (tid == 0) {
+                bulk_s2g(H + q0 * 9, out, out_bytes);
+                bulk_commit();
+            }
+        } else {   // ragged last tile: size is not a 16-byte multiple
+            for (int e = tid; e < cnt * 9; e += TILE)
+                H[q0 * 9 + e] = out[e];
+            if (tid == 0)
+                bulk_commit();   // empty group keeps the one-group-per-tile count
+        }
+        if (++s == stages) {
+            s = 0;
+            parity ^= 1;
+        }
+    }
+    if (tid == 0)
+        bulk_wait_all<0>();
+}
+
+// ------------------------------------------------------------------- k_soa
+// VEC: 16-byte vector path (Q = 4 fp32 / 2 fp64 consecutive quadruples per
+// thread); !VEC: one quadruple per thread, scalar accesses (any ld/alignment).
+template <int SOLVER, typename T, int THREADS, bool VEC>
+__global__ void __launch_bounds__(THREADS)
+k_soa(const T* __restrict__ src, const T* __restrict__ tar, const T* __restrict__ M,
+      RectParams<T> rp, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, int64_t ld,
+      bool normalize)
+{
+    constexpr int Q = VEC ? ChunkTraits<T>::EPC : 1;
+    const int64_t i0 = ((int64_t)blockIdx.x * THREADS + threadIdx.x) * Q;
+    if (i0 >= n)
+        return;
+    if (VEC && i0 + Q <= n) {
+        Chunk16 cs[8], ct[8], cm[2];
+        if constexpr (SOLVER != SOLVER_RECT) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                cs[k] = ldg_stream(src + k * ld + i0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            ct[k] = ldg_stream(tar + k * ld + i0);
+        const bool per_m = (SOLVER == SOLVER_RECT) && M != nullptr;
+        if (per_m) {
+            cm[0] = ldg_stream(M + i0);
+            cm[1] = ldg_stream(M + ld + i0);
+        }
+        Chunk16 co[9];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            T s[8], t[8], h[9];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (SOLVER != SOLVER_RECT)
+                    s[k] = ChunkTraits<T>::get(cs[k], q);
+                t[k] = ChunkTraits<T>::get(ct[k], q);
+            }
+            T mx = rp.mx, my = rp.my;
+            if (per_m) {
+                mx = ChunkTraits<T>::get(cm[0], q);
+                my = ChunkTraits<T>::get(cm[1], q);
+            }
+            solve_quad<SOLVER, T>(s, t, mx, my, rp, h, normalize);
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                ChunkTraits<T>::set(co[k], q, h[k]);
+            if (degen != nullptr)
+                degen[i0 + q] = is_degenerate<T>(h, normalize) ? 1 : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            stg_stream(H + k * ld + i0, co[k]);
+    } else {
+        const int64_t end = (i0 + Q < n) ? (i0 + Q) : n;
+        for (int64_t i = i0; i < end; ++i) {
+            T s[8], t[8], h[9];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (SOLVER != SOLVER_RECT)
+                    s[k] = __ldg(src + k * ld + i);
+                t[k] = __ldg(tar + k * ld + i);
+            }
+            T mx = rp.mx, my = rp.my;
+            if constexpr (SOLVER == SOLVER_RECT)
+                if (M != nullptr) {
+                    mx = __ldg(M + i);
+                    my = __ldg(M + ld + i);
+                }
+            solve_quad<SOLVER, T>(s, t, mx, my, rp, h, normalize);
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                H[k * ld + i] = h[k];
+            if (degen != nullptr)
+                degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
+        }
+    }
+}
+
+}  // namespace sksb

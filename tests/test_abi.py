@@ -1,0 +1,88 @@
+"""CPU tests of the drop-in boundary: libsks_cuda.so builds with nvcc alone, loads,
+exports every symbol include/sks_cuda.h declares, validates arguments, and fails
+loudly (never silently falls back) when no GPU is present."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import sks_homography_b200 as pkg
+from sks_homography_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol(sks):
+    declared = pkg.declared_symbols()
+    assert len(declared) >= 30
+    raw = C.CDLL(sks.path)
+    missing = [n for n in declared if not hasattr(raw, n)]
+    assert not missing, missing
+    assert set(_lib._SIGS) == set(declared)          # the binding covers the whole ABI
+    assert sks.c.sks_cuda_abi_version() == 1
+
+
+def test_library_is_sm100a_with_bulk_copy_kernels(sks):
+    """The shipped object carries sm_100a SASS with UBLKCP (cp.async.bulk) in the
+    ring kernels -- evidence for the TMA-staged AoS path without needing a GPU."""
+    exe = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", sks.path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out and "SYNCS" in out
+    assert "HMMA" not in out and "UTCHMMA" not in out       # deliberately no tensor cores
+
+
+def test_shard_range_is_a_partition(sks):
+    for n in (0, 1, 7, 64, 1000003, 2**28):
+        for w in (1, 2, 3, 4, 8):
+            pos = 0
+            for r in range(w):
+                b, c = sks.shard_range(n, r, w)
+                assert b == pos and c in (n // w, n // w + 1)
+                pos += c
+            assert pos == n
+    b, c = C.c_int64(), C.c_int64()
+    assert sks.c.sks_cuda_shard_range(10, 3, 3, C.byref(b), C.byref(c)) == _lib.ERR_INVALID_ARG
+
+
+def test_error_strings(sks):
+    assert sks.error_string(0) == "success"
+    assert "CPU fallback" in sks.error_string(_lib.ERR_NO_DEVICE)
+    assert "aligned" in sks.error_string(_lib.ERR_UNALIGNED)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_device_is_a_loud_error(sks):
+    a = np.zeros(32, np.float32)
+    p = a.ctypes.data
+    assert sks.c.sks_cuda_aca_f32(p, p, p, 1, 0, 0, 1, None, None) == _lib.ERR_NO_DEVICE
+    assert sks.c.sks_host_sks_f32(p, p, p, 1, 1) == _lib.ERR_NO_DEVICE
+    from sks_homography_b200 import api
+    with pytest.raises(pkg.SksCudaError):
+        api.runKernel_ACA(torch.zeros(1, 8), torch.zeros(1, 8))
+
+
+def test_argument_validation_precedes_device_use(sks):
+    a = np.zeros(32, np.float32)
+    p = a.ctypes.data
+    assert sks.c.sks_cuda_aca_f32(p, p, p, -1, 0, 0, 1, None, None) == _lib.ERR_INVALID_ARG
+    assert sks.c.sks_cuda_aca_f32(p, p, p, 1, 7, 0, 1, None, None) == _lib.ERR_INVALID_ARG
+    assert sks.c.sks_cuda_aca_f32(p, p, p, 1, 0, 0, 99, None, None) == _lib.ERR_INVALID_ARG
+    assert sks.c.sks_cuda_aca_f32(None, p, p, 1, 0, 0, 1, None, None) == _lib.ERR_INVALID_ARG
+    assert sks.c.sks_cuda_set_variant(5) == _lib.ERR_INVALID_ARG
+    assert sks.c.sks_cuda_set_tuning(0, 1, 0) == _lib.ERR_INVALID_ARG
+    assert sks.c.sks_cuda_set_tuning(0, 4, 0) == 0
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it."""
+    root = os.path.dirname(os.path.abspath(pkg.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "libsks_oracle" not in text and "libsks_ref" not in text, f

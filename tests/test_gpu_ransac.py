@@ -1,0 +1,79 @@
+"""GPU tests of the fused ACA-RANSAC kernel: inlier counts and winners bit-exact
+against the CPU oracle for a fixed seed and for an explicit sample list."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def api(sks, cuda):
+    from sks_homography_b200 import api as a
+    return a
+
+
+def u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("n_pts,n_hyp", [(4096, 2048), (1000, 777), (64, 5), (9000, 600)])
+def test_keys_match_oracle_seeded(api, oracle, cuda, n_pts, n_hyp):
+    P = 6
+    corr = api.synth_corr(P, n_pts, seed=3, inlier_permille=550, noise=0.5, device=cuda)
+    keys = api.ransac_keys(corr, n_hyp, seed=77, thr2=2.25)
+    want = oracle.ransac(corr.cpu().numpy(), n_hyp, seed=77, thr2=2.25)
+    assert np.array_equal(u64(keys), want)
+    cnt, hyp = api.decode_keys(keys)
+    assert (cnt.cpu().numpy() > 0.3 * n_pts).all() or n_hyp < 50
+
+
+def test_per_hypothesis_counts_bit_exact(api, oracle, cuda):
+    """Every hypothesis, not just the winner: score single-hypothesis ranges."""
+    P, n_pts, n_hyp = 2, 512, 96
+    corr = api.synth_corr(P, n_pts, seed=9, device=cuda)
+    _, counts = oracle.ransac(corr.cpu().numpy(), n_hyp, seed=5, thr2=4.0, want_counts=True)
+    got = np.zeros_like(counts)
+    for j in range(n_hyp):
+        k = api.ransac_keys(corr, n_hyp, seed=5, thr2=4.0, hyp_begin=j, hyp_count=1)
+        got[:, j] = (u64(k) >> np.uint64(32)).astype(np.uint32)
+    assert np.array_equal(got, counts)
+
+
+def test_explicit_sample_list(api, oracle, cuda):
+    P, n_pts, n_hyp = 3, 2048, 1024
+    corr = api.synth_corr(P, n_pts, seed=4, device=cuda)
+    rng = np.random.default_rng(8)
+    samples = rng.integers(0, n_pts, size=(P, n_hyp, 4), dtype=np.uint32)
+    samples[:, 5] = samples[:, 5, :1]                     # a repeated-index (degenerate) sample
+    keys = api.ransac_keys(corr, n_hyp, seed=0, thr2=4.0, samples=torch.from_numpy(samples).to(cuda))
+    want = oracle.ransac(corr.cpu().numpy(), n_hyp, seed=0, thr2=4.0, samples=samples)
+    assert np.array_equal(u64(keys), want)
+
+
+def test_ranges_merge_and_finalize(api, oracle, cuda):
+    P, n_pts, n_hyp = 5, 4096, 4096
+    corr = api.synth_corr(P, n_pts, seed=6, device=cuda)
+    full = api.ransac_keys(corr, n_hyp, seed=1, thr2=2.25)
+    keys = torch.zeros(P, dtype=torch.int64, device=cuda)
+    for b, c in ((0, 1000), (1000, 2000), (3000, 1096)):        # what 3 GPUs would each score
+        api.ransac_keys(corr, n_hyp, seed=1, thr2=2.25, hyp_begin=b, hyp_count=c, out=keys)
+    assert torch.equal(keys, full)
+    H, cnt, mask = api.ransac_finalize(corr, n_hyp, 1, 2.25, keys, want_mask=True)
+    kc, hyp = api.decode_keys(keys)
+    assert torch.equal(cnt.long(), kc) and torch.equal(mask.sum(1).long(), kc)
+    c_np = corr.cpu().numpy()
+    for p in range(P):
+        idx = oracle.ransac_sample(1, p, int(hyp[p]), n_pts)
+        Hw = oracle.ransac_hypothesis(c_np[p], idx)
+        assert np.array_equal(H[p].cpu().numpy().view(np.uint32), Hw.view(np.uint32))
+        assert oracle.ransac_count(Hw, c_np[p], 2.25) == int(cnt[p])
+
+
+def test_dist_driver_single_rank(api, cuda):
+    from sks_homography_b200 import dist as sd
+    corr = api.synth_corr(4, 1024, seed=2, device=cuda)
+    H, cnt, hyp, _ = sd.ransac_aca(corr, 512, seed=3, thr2=4.0)
+    keys = api.ransac_keys(corr, 512, seed=3, thr2=4.0)
+    kc, kh = api.decode_keys(keys)
+    assert torch.equal(cnt.long(), kc) and torch.equal(hyp, kh)
