@@ -166,7 +166,7 @@ int sks_cuda_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t
  * reset (bench.py reports it as gpu_launches). */
 int64_t sks_cuda_launch_count(void);
 void sks_cuda_reset_launch_count(void);
-/* Kernel variant for the AoS streaming solvers: 0 = default (best measured),
+/* Kernel variant for the AoS streaming solvers: 0 = default (best measured, = 1),
  * 1 = direct vector loads + shared-memory transposed stores,
  * 2 = persistent TMA bulk-copy ring (cp.async.bulk + mbarrier).  A tuning knob
  * for bench.py sweeps, not a backend switch: every variant is sm_100a CUDA. */

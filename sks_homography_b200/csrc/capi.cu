@@ -89,13 +89,14 @@ template <int SOLVER, typename T>
 int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, int64_t n,
                   int layout, int64_t ld, int flags, uint8_t* degen, void* stream)
 {
-    if (n < 0 || H == nullptr || tar == nullptr) return SKS_ERR_INVALID_ARG;
-    if (SOLVER != SOLVER_RECT && src == nullptr) return SKS_ERR_INVALID_ARG;
+    if (n < 0) return SKS_ERR_INVALID_ARG;
     if (layout != SKS_LAYOUT_AOS && layout != SKS_LAYOUT_SOA) return SKS_ERR_INVALID_ARG;
     if (flags & ~SKS_FLAG_NORMALIZE) return SKS_ERR_INVALID_ARG;
+    if (n > 0 && (H == nullptr || tar == nullptr)) return SKS_ERR_INVALID_ARG;
+    if (n > 0 && SOLVER != SOLVER_RECT && src == nullptr) return SKS_ERR_INVALID_ARG;
     DevInfo dev;
     if (int rc = device_info(dev)) return rc;
-    if (n == 0) return SKS_OK;
+    if (n == 0) return SKS_OK;   // empty batch: nothing to enqueue (buffers may be NULL)
     if (!aligned16(H) || !aligned16(tar) || (src && !aligned16(src)) || (M && !aligned16(M)))
         return SKS_ERR_UNALIGNED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -120,7 +121,7 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
     }
 
     int variant = g_variant.load();
-    if (variant == 0) variant = 2;
+    if (variant == 0) variant = 1;   // measured best on B200 (profiles/): direct > ring
     constexpr int BIG = sizeof(T) == 4 ? 256 : 128;
     constexpr int SMALL = BIG / 2;
     if (variant == 1) {
