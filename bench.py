@@ -119,6 +119,9 @@ def run_reference(args):
         return 0
     import numpy as np
     from oracle.oracle import Oracle, RefLib
+    if args.workload == "ransac":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has no RANSAC scorer"}))
+        return 0
     solver, dt, bytes_per_h, log2n, dist = WORKLOADS[args.workload]
     if solver == "rect":
         print(json.dumps({"impl": "reference", "unavailable": "the reference has no C++ ACA-rect"}))
@@ -166,7 +169,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="aca_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="aca_f32", choices=sorted(WORKLOADS) + ["ransac"])
+    ap.add_argument("--pairs", type=int, default=1024)
+    ap.add_argument("--points", type=int, default=4096)
+    ap.add_argument("--hyps", type=int, default=65536)
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--log2n", type=int, default=None, help="quadruples per GPU = 2^log2n")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--no-normalize", action="store_true")
@@ -206,6 +213,9 @@ def main():
     L = lib()
     L.check(L.c.sks_cuda_set_variant(args.variant), "set_variant")
     L.check(L.c.sks_cuda_set_tuning(args.small_tile, args.stages, args.ctas), "set_tuning")
+
+    if args.workload == "ransac":
+        return run_ransac(args, api, L, dev, rank, world, local)
 
     solver, dt, bytes_per_h, log2n, dist_id = WORKLOADS[args.workload]
     log2n = args.log2n if args.log2n is not None else log2n
@@ -334,6 +344,10 @@ def main():
                          f"MOD/ACA_SKS.cpp g++ -O2 -ffp-contract=off, {threads} threads",
                "parity_gpu_vs_cpu": parity}
 
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu and not args.no_gpu_baseline:
+        gpu_base = reference_gpu_kernels(api, dev)
+
     if rank == 0:
         line = {
             "impl": "ours", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -347,7 +361,153 @@ def main():
                        "l2": f"inputs+outputs {n * bytes_per_h / 1e9:.2f} GB per step >> 126 MB L2, no flush needed",
                        "seed": args.seed, "dist": dist_id},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks,
+            "clocks": clocks, "gpu_baseline": gpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _event_ms(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    return ts[len(ts) // 2]
+
+
+def reference_gpu_kernels(api, dev):
+    """Same-box GPU comparator: the reference's own CUDA kernels (GPU.cu:81-240,
+    compiled for sm_100a at build time into oracle/_ref) launched as the reference
+    does -- fp64, SoA, <<<ceil(N/32),32>>>, un-normalised -- next to ours on the same
+    buffers.  N = 2^20 is the largest row of the paper's Table 8; 2^25 is config 4."""
+    import torch
+    try:
+        from oracle.oracle import RefGpuLib
+        ref = RefGpuLib()
+    except Exception as e:                                   # not built: report, do not fail
+        return {"unavailable": str(e)[:120]}
+    out = {"kernels": "GPU_Runtime Test.cu:81-240 cal_Homo_ACA/SKS, nvcc -O3 sm_100a, block 32, "
+                      "fp64 SoA un-normalised", "rows": []}
+    for log2n in (20, 25):
+        n = 1 << log2n
+        src, tar = api.synth_quads(n, 11, 1, torch.float64, dev, layout="soa")
+        H = torch.empty((9, n), dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        for solver in ("aca", "sks"):
+            t_ref = _event_ms(lambda: ref.run(solver, src.data_ptr(), tar.data_ptr(), H.data_ptr(), n, st), 20)
+            t_our = _event_ms(lambda: api.solve(solver, src, tar, result=H, normalize=False, layout="soa"), 20)
+            out["rows"].append({"solver": solver, "n": n, "reference_us": 1e3 * t_ref, "ours_us": 1e3 * t_our,
+                                "reference_GHps": n / t_ref / 1e6, "ours_GHps": n / t_our / 1e6,
+                                "reference_GBps": n * 200 / t_ref / 1e6, "ours_GBps": n * 200 / t_our / 1e6})
+        del src, tar, H
+    return out
+
+
+def run_ransac(args, api, L, dev, rank, world, local):
+    """BASELINE configs[4]: fused ACA-RANSAC, P pairs x n_pts matches x n_hyp
+    hypotheses.  Multi-GPU variant (A) of SURVEY.md 8(e): every rank holds all
+    pairs' matches and scores its contiguous shard of the hypothesis ids; ONE
+    int64 max-all-reduce (NCCL over NVLink) merges the winners; the winning model
+    is recomputed locally.  Strong scaling: total work is fixed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sks_homography_b200 import dist as sd
+
+    P, n_pts, n_hyp = args.pairs, args.points, args.hyps
+    thr2 = 2.25
+    corr = api.synth_corr(P, n_pts, seed=args.seed, inlier_permille=500, noise=0.5, device=dev)
+    hb, hc = sd.shard_range(n_hyp, rank, world)
+    keys = torch.zeros(P, dtype=torch.int64, device=dev)
+    res = {}
+
+    def step():
+        keys.zero_()
+        api.ransac_keys(corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys)
+        sd.merge_keys(keys)
+        res["H"], res["cnt"], _ = api.ransac_finalize(corr, n_hyp, args.seed, thr2, keys)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.c.sks_cuda_reset_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    launches = int(L.c.sks_cuda_launch_count())
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.stop() if sampler else None
+    barrier()
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    value = P * n_hyp / (ms_per_step * 1e-3)
+
+    # FP32 roofline: 22 flop per hypothesis x point + 97 per hypothesis (SURVEY.md 8(d))
+    flops = P * float(n_hyp) * (97.0 + 22.0 * n_pts)
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 128 * 2 * mhz * 1e6 / 1e12 * world
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": f"148 SM x 128 lanes x 2 x {mhz:.0f} MHz (SM clock sampled under load) x {world} GPU",
+                "flop_per_hypothesis_point": 22, "flop_per_hypothesis": 97}
+
+    # parity at full size: a few pairs against the CPU oracle on a hypothesis prefix,
+    # and (multi-GPU) merged keys == single-GPU keys on the same pairs
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle.oracle import Oracle
+        o = Oracle()
+        sel = [0, P // 2, P - 1]
+        sub = corr[sel].contiguous()
+        nh = min(n_hyp, 2048)
+        got = api.ransac_keys(sub, n_hyp, args.seed, thr2, None, 0, nh).cpu().numpy().view(np.uint64)
+        want = o.ransac(sub.cpu().numpy(), nh, args.seed, thr2)      # same pair ids 0..2, hyps 0..nh-1
+        full1 = None
+        if world > 1:
+            full1 = api.ransac_keys(sub, n_hyp, args.seed, thr2)
+            k2 = torch.zeros(3, dtype=torch.int64, device=dev)
+            for r in range(world):
+                b, c = sd.shard_range(n_hyp, r, world)
+                api.ransac_keys(sub, n_hyp, args.seed, thr2, None, b, c, out=k2)
+            full1 = bool(torch.equal(full1, k2))
+        parity = {"pairs_checked": 3, "hypotheses_checked": nh,
+                  "keys_equal_cpu_oracle": bool(np.array_equal(got, want)),
+                  "sharded_equals_unsharded": full1}
+    if rank == 0:
+        cnt = res["cnt"].float()
+        line = {
+            "impl": "ours", "metric": "ACA-RANSAC hypotheses/s (homographies solved and scored)",
+            "value": value, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fused ACA-RANSAC {P} pairs x {n_pts} matches x {n_hyp} hypotheses, "
+                                   f"hypotheses sharded over {world} GPU(s), one int64 max all-reduce",
+                       "thr2": thr2, "seed": args.seed,
+                       "l2": "compute-bound; matches (64 KiB/pair) live in shared memory"},
+            "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
+            "clocks": clocks, "parity": parity,
+            "mean_inlier_fraction_of_winner": float(cnt.mean().item()) / n_pts,
         }
         print(json.dumps(line))
     if world > 1:

@@ -19,13 +19,14 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libsks_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsks_ref.so")
+REFGPU_SO = os.path.join(HERE, "_ref", "libsks_refgpu.so")
 REFERENCE_ROOT = "/root/reference"
 
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference checkout exists)."""
     need = force or not os.path.exists(ORACLE_SO)
-    if os.path.isdir(REFERENCE_ROOT) and not os.path.exists(REF_SO):
+    if os.path.isdir(REFERENCE_ROOT) and not (os.path.exists(REF_SO) and os.path.exists(REFGPU_SO)):
         need = True
     if need:
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True,
@@ -162,3 +163,25 @@ class RefLib:
         fn = getattr(self.lib, f"ref_{solver}_{'f32' if dt == np.float32 else 'f64'}")
         fn(_p(src), _p(tar), _p(H), C.c_int64(n), C.c_int(threads))
         return H
+
+
+class RefGpuLib:
+    """The reference's own CUDA kernels (GPU.cu:81-240, extracted and compiled for
+    sm_100a at build time by oracle/Makefile) behind their reference launch shape
+    <<<ceil(N/32),32>>>: fp64, SoA, un-normalised.  Perf comparator only."""
+
+    def __init__(self):
+        if not os.path.exists(REFGPU_SO):
+            build()
+        if not os.path.exists(REFGPU_SO):
+            raise FileNotFoundError(REFGPU_SO)
+        self.lib = C.CDLL(REFGPU_SO)
+        for name in ("refgpu_aca_f64", "refgpu_sks_f64"):
+            fn = getattr(self.lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+
+    def run(self, solver: str, d_src: int, d_tar: int, d_H: int, n: int, stream: int) -> None:
+        rc = getattr(self.lib, f"refgpu_{solver}_f64")(d_src, d_tar, d_H, n, stream)
+        if rc != 0:
+            raise RuntimeError(f"reference CUDA kernel launch failed: cudaError {rc}")
