@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--points", type=int, default=4096)
     ap.add_argument("--hyps", type=int, default=65536)
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--hpt", type=int, default=0, help="RANSAC hypotheses per thread (2|4)")
+    ap.add_argument("--rounds", type=int, default=8, help="RANSAC rounds per CTA")
     ap.add_argument("--log2n", type=int, default=None, help="quadruples per GPU = 2^log2n")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--no-normalize", action="store_true")
@@ -215,6 +217,8 @@ def main():
     L.check(L.c.sks_cuda_set_tuning(args.small_tile, args.stages, args.ctas), "set_tuning")
 
     if args.workload == "ransac":
+        if args.hpt:
+            L.check(L.c.sks_cuda_set_ransac_tuning(args.hpt, args.rounds), "set_ransac_tuning")
         return run_ransac(args, api, L, dev, rank, world, local)
 
     solver, dt, bytes_per_h, log2n, dist_id = WORKLOADS[args.workload]

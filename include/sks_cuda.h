@@ -176,6 +176,9 @@ int sks_cuda_get_variant(void);
  * 1: half of that), stages (2..16 shared-memory ring slots), ctas_per_sm
  * (0 = as many as fit). */
 int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm);
+/* RANSAC kernel tuning: hypotheses carried per thread (2 or 4) and scoring rounds
+ * per CTA (a CTA scores rounds*256*hyps_per_thread hypothesis ids). */
+int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta);
 int sks_cuda_shutdown(void);
 
 #ifdef __cplusplus

@@ -22,6 +22,8 @@ std::atomic<int> g_variant{0};        // 0 default, 1 direct, 2 ring
 std::atomic<int> g_tile_small{0};     // ring tile: 0 = 256/128 (f32/f64), 1 = 128/64
 std::atomic<int> g_stages{4};
 std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
+std::atomic<int> g_ransac_hpt{2};     // hypotheses per thread in the RANSAC kernel (2 or 4)
+std::atomic<int> g_ransac_rounds{8};  // rounds per CTA (chunk = rounds * 256 * hpt hypotheses)
 
 struct DevInfo {
     int sms = 0;
@@ -250,18 +252,20 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
     if (n_pairs == 0 || hyp_count == 0) return SKS_OK;
     const int32_t tile_pts = n_pts < kRansacMaxTilePts ? n_pts : kRansacMaxTilePts;
     const int smem = tile_pts * 16;
-    cudaError_t e = cudaFuncSetAttribute(k_ransac_aca, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int hpt = g_ransac_hpt.load();
+    auto kern = hpt == 4 ? k_ransac_aca<4> : k_ransac_aca<2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     // chunk: enough hypotheses per CTA to amortise the tile load, enough CTAs
     // to fill the machine several times over
-    const uint32_t round = kRansacThreads * kRansacHpt;
-    uint32_t chunk = round * 8;
+    const uint32_t round = kRansacThreads * (uint32_t)hpt;
+    uint32_t chunk = round * (uint32_t)g_ransac_rounds.load();
     while (chunk > round &&
            (int64_t)((hyp_count + chunk - 1) / chunk) * n_pairs < (int64_t)dev.sms * 8)
         chunk -= round;
     const unsigned chunks = (hyp_count + chunk - 1) / chunk;
     dim3 grid(chunks, (unsigned)n_pairs);
-    k_ransac_aca<<<grid, kRansacThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    kern<<<grid, kRansacThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(corr), n_pts, tile_pts, samples, hyp_stride, hyp_begin,
         hyp_count, chunk, seed_key(seed), thr2, best_key);
     return finish_launch();
@@ -330,6 +334,15 @@ int sks_cuda_set_variant(int variant)
     return SKS_OK;
 }
 int sks_cuda_get_variant(void) { return g_variant.load(); }
+
+int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta)
+{
+    if ((hyps_per_thread != 2 && hyps_per_thread != 4) || rounds_per_cta < 1 || rounds_per_cta > 1024)
+        return SKS_ERR_INVALID_ARG;
+    g_ransac_hpt.store(hyps_per_thread);
+    g_ransac_rounds.store(rounds_per_cta);
+    return SKS_OK;
+}
 
 int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm)
 {

@@ -9,7 +9,13 @@
 //     u = fma(h0,x,fma(h1,y,h2));  v = fma(h3,x,fma(h4,y,h5));
 //     w = fma(h6,x,fma(h7,y,h8));
 //     du = fma(X,w,-u); dv = fma(Y,w,-v); e = fma(dv,dv,du*du)
-//     inlier <=> e < (thr2*w)*w          (division-free forward transfer error)
+//     acc = fma(-(thr2*w), w, e);  inlier <=> acc < 0
+//   (division-free forward transfer error |proj(x) - X|^2 < thr2, both sides
+//   multiplied by w^2).  On the GPU "acc < 0" is read off the sign bit and added
+//   to the count with one integer instruction: acc is never -0 (e >= +0 and an
+//   exact cancellation rounds to +0) and a NaN acc is the canonical positive NaN
+//   on NVIDIA hardware, so the sign bit is exactly the IEEE comparison the
+//   oracle evaluates.
 //
 // Mapping: a CTA owns one image pair and a contiguous chunk of hypothesis ids.
 // The pair's correspondences (x,y,X,Y) are pulled into shared memory once by
@@ -29,7 +35,6 @@
 namespace sksb {
 
 constexpr int kRansacThreads = 256;
-constexpr int kRansacHpt = 2;              // hypotheses per thread per round
 constexpr int kRansacMaxTilePts = 8192;    // 128 KiB of shared memory at most
 
 __device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, uint32_t hyp,
@@ -61,7 +66,8 @@ __device__ __forceinline__ void ransac_hypothesis(const float4* __restrict__ cor
     aca_solve<float>(s, t, h, true);
 }
 
-__device__ __forceinline__ bool ransac_inlier(const float (&h)[9], const float4 c, float thr2)
+// 1 if the match is an inlier of h, else 0 (sign bit of acc, see header)
+__device__ __forceinline__ uint32_t ransac_inlier(const float (&h)[9], const float4 c, float thr2)
 {
     const float u = __fmaf_rn(h[0], c.x, __fmaf_rn(h[1], c.y, h[2]));
     const float v = __fmaf_rn(h[3], c.x, __fmaf_rn(h[4], c.y, h[5]));
@@ -69,8 +75,8 @@ __device__ __forceinline__ bool ransac_inlier(const float (&h)[9], const float4 
     const float du = __fmaf_rn(c.z, w, -u);
     const float dv = __fmaf_rn(c.w, w, -v);
     const float e = __fmaf_rn(dv, dv, __fmul_rn(du, du));
-    const float lim = __fmul_rn(__fmul_rn(thr2, w), w);
-    return e < lim;
+    const float acc = __fmaf_rn(-__fmul_rn(thr2, w), w, e);
+    return __float_as_uint(acc) >> 31;
 }
 
 __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_t hyp)
@@ -80,6 +86,7 @@ __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_
 
 // grid = (chunks_per_pair, n_pairs); each CTA scores hypothesis ids
 // [hyp_begin + chunk*chunk_size, +chunk_size) ∩ [hyp_begin, hyp_begin+hyp_count)
+template <int kRansacHpt>   // hypotheses carried per thread per round
 __global__ void __launch_bounds__(kRansacThreads)
 k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
              const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
@@ -149,13 +156,13 @@ k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int j = 0; j < kRansacHpt; ++j)
-                        cnt[j] += ransac_inlier(h[j], c[k], thr2) ? 1u : 0u;
+                        cnt[j] += ransac_inlier(h[j], c[k], thr2);
             }
             for (; i < np; ++i) {
                 const float4 c = tile[i];
 #pragma unroll
                 for (int j = 0; j < kRansacHpt; ++j)
-                    cnt[j] += ransac_inlier(h[j], c, thr2) ? 1u : 0u;
+                    cnt[j] += ransac_inlier(h[j], c, thr2);
             }
             if (n_tiles > 1) {   // stream the next tile (wraps for the next round)
                 __syncthreads();
@@ -222,8 +229,8 @@ k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
         h[k] = hs[k];
     uint32_t mine = 0;
     for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
-        const bool in = ransac_inlier(h, __ldg(corr_pair + i), thr2);
-        mine += in ? 1u : 0u;
+        const uint32_t in = ransac_inlier(h, __ldg(corr_pair + i), thr2);
+        mine += in;
         if (inlier_mask != nullptr)
             inlier_mask[(size_t)pair * n_pts + i] = in ? 1 : 0;
     }

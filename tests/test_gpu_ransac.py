@@ -77,3 +77,29 @@ def test_dist_driver_single_rank(api, cuda):
     keys = api.ransac_keys(corr, 512, seed=3, thr2=4.0)
     kc, kh = api.decode_keys(keys)
     assert torch.equal(cnt.long(), kc) and torch.equal(hyp, kh)
+
+
+@pytest.mark.parametrize("hpt", [2, 4])
+def test_nonfinite_scores_are_never_inliers(api, sks, oracle, cuda, hpt):
+    """Overflowing / NaN hypotheses and matches: the GPU reads the inlier bit off the
+    sign of acc, the oracle evaluates acc < 0; both must ignore NaN and +-inf alike."""
+    assert sks.c.sks_cuda_set_ransac_tuning(hpt, 8) == 0
+    try:
+        rng = np.random.default_rng(12)
+        P, n_pts, n_hyp = 3, 1024, 1536
+        corr = api.synth_corr(P, n_pts, seed=21, device=cuda).cpu().numpy()
+        corr[0, ::7] *= 1e18          # products overflow to inf, inf - inf = NaN
+        corr[1, ::5, 2:] = np.inf
+        corr[2, ::3] = np.nan
+        corr[2, 1::3, :2] = corr[2, 4, :2] if np.isfinite(corr[2, 4, 0]) else 1.0   # repeated points
+        c = torch.from_numpy(corr).to(cuda)
+        keys = api.ransac_keys(c, n_hyp, seed=2, thr2=4.0)
+        want, counts = oracle.ransac(corr, n_hyp, seed=2, thr2=4.0, want_counts=True)
+        assert np.array_equal(u64(keys), want)
+        got = np.zeros_like(counts)
+        for j in range(0, n_hyp, 97):
+            k = api.ransac_keys(c, n_hyp, seed=2, thr2=4.0, hyp_begin=j, hyp_count=1)
+            got[:, j] = (u64(k) >> np.uint64(32)).astype(np.uint32)
+            assert np.array_equal(got[:, j], counts[:, j])
+    finally:
+        sks.c.sks_cuda_set_ransac_tuning(2, 8)
