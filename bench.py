@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--hpt", type=int, default=0, help="RANSAC hypotheses per thread (2|4)")
     ap.add_argument("--rounds", type=int, default=8, help="RANSAC rounds per CTA")
+    ap.add_argument("--packed", type=int, default=-1, help="RANSAC FFMA2 scoring (0|1)")
     ap.add_argument("--log2n", type=int, default=None, help="quadruples per GPU = 2^log2n")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--no-normalize", action="store_true")
@@ -217,8 +218,9 @@ def main():
     L.check(L.c.sks_cuda_set_tuning(args.small_tile, args.stages, args.ctas), "set_tuning")
 
     if args.workload == "ransac":
-        if args.hpt:
-            L.check(L.c.sks_cuda_set_ransac_tuning(args.hpt, args.rounds), "set_ransac_tuning")
+        if args.hpt or args.packed >= 0:
+            L.check(L.c.sks_cuda_set_ransac_tuning(args.hpt or 2, args.rounds, max(args.packed, 0)),
+                    "set_ransac_tuning")
         return run_ransac(args, api, L, dev, rank, world, local)
 
     solver, dt, bytes_per_h, log2n, dist_id = WORKLOADS[args.workload]
@@ -279,7 +281,9 @@ def main():
     # ---- end to end through the host-pointer C ABI ------------------------------
     e2e = None
     if not args.no_e2e and args.layout == "aos":
-        ne = 1 << (args.e2e_log2n if args.e2e_log2n is not None else log2n)
+        # 2^25 quadruples per GPU per step by default: 3.4 GB of pinned host memory per
+        # rank, so 8 ranks stay far below the host's RAM (the kernel-only `value` keeps 2^26)
+        ne = 1 << (args.e2e_log2n if args.e2e_log2n is not None else min(log2n, 25))
         ne = min(ne, n)
         hs = torch.empty((ne, 8), dtype=tdt, pin_memory=True)
         ht = torch.empty((ne, 8), dtype=tdt, pin_memory=True)

@@ -68,7 +68,7 @@ _SIGS = {
     "sks_cuda_set_variant": (_int, [_int]),
     "sks_cuda_get_variant": (_int, []),
     "sks_cuda_set_tuning": (_int, [_int, _int, _int]),
-    "sks_cuda_set_ransac_tuning": (_int, [_int, _int]),
+    "sks_cuda_set_ransac_tuning": (_int, [_int, _int, _int]),
     "sks_cuda_shutdown": (_int, []),
 }
 

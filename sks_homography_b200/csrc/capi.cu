@@ -23,6 +23,8 @@ std::atomic<int> g_tile_small{0};     // ring tile: 0 = 256/128 (f32/f64), 1 = 1
 std::atomic<int> g_stages{4};
 std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
 std::atomic<int> g_ransac_hpt{2};     // hypotheses per thread in the RANSAC kernel (2 or 4)
+std::atomic<int> g_ransac_packed{1};  // 1 = FFMA2/FMUL2 two-matches-per-instruction scoring (measured best)
+std::atomic<int> g_ransac_threads{256};
 std::atomic<int> g_ransac_rounds{8};  // rounds per CTA (chunk = rounds * 256 * hpt hypotheses)
 
 struct DevInfo {
@@ -251,21 +253,34 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
     if (int rc = device_info(dev)) return rc;
     if (n_pairs == 0 || hyp_count == 0) return SKS_OK;
     const int32_t tile_pts = n_pts < kRansacMaxTilePts ? n_pts : kRansacMaxTilePts;
-    const int smem = tile_pts * 16;
+    const int smem = ((tile_pts + 1) & ~1) * 16;
     const int hpt = g_ransac_hpt.load();
-    auto kern = hpt == 4 ? k_ransac_aca<4> : k_ransac_aca<2>;
+    const bool packed = g_ransac_packed.load() != 0;
+    const int threads = g_ransac_threads.load();
+    using Kern = void (*)(const float4*, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
+                          uint32_t, uint32_t, uint64_t, float, unsigned long long*);
+    Kern kern;
+    if (threads == 512)
+        kern = packed ? (hpt == 4 ? k_ransac_aca<4, true, 512> : k_ransac_aca<2, true, 512>)
+                      : (hpt == 4 ? k_ransac_aca<4, false, 512> : k_ransac_aca<2, false, 512>);
+    else if (threads == 384)
+        kern = packed ? (hpt == 4 ? k_ransac_aca<4, true, 384> : k_ransac_aca<2, true, 384>)
+                      : (hpt == 4 ? k_ransac_aca<4, false, 384> : k_ransac_aca<2, false, 384>);
+    else
+        kern = packed ? (hpt == 4 ? k_ransac_aca<4, true, 256> : k_ransac_aca<2, true, 256>)
+                      : (hpt == 4 ? k_ransac_aca<4, false, 256> : k_ransac_aca<2, false, 256>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     // chunk: enough hypotheses per CTA to amortise the tile load, enough CTAs
     // to fill the machine several times over
-    const uint32_t round = kRansacThreads * (uint32_t)hpt;
+    const uint32_t round = (uint32_t)threads * (uint32_t)hpt;
     uint32_t chunk = round * (uint32_t)g_ransac_rounds.load();
     while (chunk > round &&
            (int64_t)((hyp_count + chunk - 1) / chunk) * n_pairs < (int64_t)dev.sms * 8)
         chunk -= round;
     const unsigned chunks = (hyp_count + chunk - 1) / chunk;
     dim3 grid(chunks, (unsigned)n_pairs);
-    kern<<<grid, kRansacThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    kern<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(corr), n_pts, tile_pts, samples, hyp_stride, hyp_begin,
         hyp_count, chunk, seed_key(seed), thr2, best_key);
     return finish_launch();
@@ -335,12 +350,15 @@ int sks_cuda_set_variant(int variant)
 }
 int sks_cuda_get_variant(void) { return g_variant.load(); }
 
-int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta)
+int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int packed)
 {
     if ((hyps_per_thread != 2 && hyps_per_thread != 4) || rounds_per_cta < 1 || rounds_per_cta > 1024)
         return SKS_ERR_INVALID_ARG;
     g_ransac_hpt.store(hyps_per_thread);
     g_ransac_rounds.store(rounds_per_cta);
+    g_ransac_packed.store(packed & 1);
+    const int t = packed >> 1;                       // bits 1.. select the CTA size
+    g_ransac_threads.store(t == 1 ? 384 : t == 2 ? 512 : 256);
     return SKS_OK;
 }
 

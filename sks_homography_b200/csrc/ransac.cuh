@@ -34,7 +34,6 @@
 
 namespace sksb {
 
-constexpr int kRansacThreads = 256;
 constexpr int kRansacMaxTilePts = 8192;    // 128 KiB of shared memory at most
 
 __device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, uint32_t hyp,
@@ -79,6 +78,27 @@ __device__ __forceinline__ uint32_t ransac_inlier(const float (&h)[9], const flo
     return __float_as_uint(acc) >> 31;
 }
 
+// Packed form for sm_100a's 2-wide FP32 instructions (FFMA2 / FMUL2): the same
+// test on TWO matches at once.  p0 = (x0,x1,y0,y1), p1 = (-X0,-X1,-Y0,-Y1) is the
+// pair layout the kernel rewrites the shared-memory tile into; h[k] = (h_k,h_k).
+// Bit-identical to two ransac_inlier calls: each half is an IEEE fused
+// multiply-add, u - X*w is the exact negation of X*w - u (its square is the
+// same), and (-thr2)*w is the exact negation of thr2*w.
+__device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&h)[9], const float4 p0,
+                                                   const float4 p1, const float2 nthr2)
+{
+    const float2 x = make_float2(p0.x, p0.y), y = make_float2(p0.z, p0.w);
+    const float2 nX = make_float2(p1.x, p1.y), nY = make_float2(p1.z, p1.w);
+    const float2 u = __ffma2_rn(h[0], x, __ffma2_rn(h[1], y, h[2]));
+    const float2 v = __ffma2_rn(h[3], x, __ffma2_rn(h[4], y, h[5]));
+    const float2 w = __ffma2_rn(h[6], x, __ffma2_rn(h[7], y, h[8]));
+    const float2 du = __ffma2_rn(nX, w, u);
+    const float2 dv = __ffma2_rn(nY, w, v);
+    const float2 e = __ffma2_rn(dv, dv, __fmul2_rn(du, du));
+    const float2 acc = __ffma2_rn(__fmul2_rn(nthr2, w), w, e);
+    return (__float_as_uint(acc.x) >> 31) + (__float_as_uint(acc.y) >> 31);
+}
+
 __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_t hyp)
 {
     return ((unsigned long long)count << 32) | (unsigned long long)(0xFFFFFFFFu - hyp);
@@ -86,7 +106,9 @@ __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_
 
 // grid = (chunks_per_pair, n_pairs); each CTA scores hypothesis ids
 // [hyp_begin + chunk*chunk_size, +chunk_size) ∩ [hyp_begin, hyp_begin+hyp_count)
-template <int kRansacHpt>   // hypotheses carried per thread per round
+// kRansacHpt: hypotheses carried per thread per round.  PACKED: score two matches
+// per instruction with FFMA2/FMUL2 (the tile is re-laid out in pairs on arrival).
+template <int kRansacHpt, bool PACKED, int kRansacThreads>
 __global__ void __launch_bounds__(kRansacThreads)
 k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
              const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
@@ -126,6 +148,7 @@ k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
     unsigned long long best = 0ull;
     for (uint32_t base = c_lo; base < c_hi; base += kRansacThreads * kRansacHpt) {
         float h[kRansacHpt][9];
+        float2 h2[PACKED ? kRansacHpt : 1][9];
         uint32_t cnt[kRansacHpt], hyp[kRansacHpt];
         bool live[kRansacHpt];
 #pragma unroll
@@ -137,32 +160,74 @@ k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
             ransac_sample(key, pair, hyp[j], samples, hyp_stride, (uint32_t)n_pts, idx);
             ransac_hypothesis(corr_pair, idx, h[j]);
             cnt[j] = 0;
+            if constexpr (PACKED) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    h2[j][k] = make_float2(h[j][k], h[j][k]);
+            }
         }
+        const float2 nthr2 = make_float2(-thr2, -thr2);
         for (int tl = 0; tl < n_tiles; ++tl) {
+            const int lo = tl * tile_pts;
+            const int np = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
             if (!resident) {
                 mbar_wait(&bar, phase);
                 phase ^= 1;
                 resident = (n_tiles == 1);
+                if constexpr (PACKED) {
+                    // re-lay the freshly landed AoS tile out in pairs, in place:
+                    // (x0,x1,y0,y1)(-X0,-X1,-Y0,-Y1); an odd tail is padded with a
+                    // NaN target that can never be an inlier
+                    const float qnan = __int_as_float(0x7fffffff);
+                    for (int p = tid; 2 * p < np; p += kRansacThreads) {
+                        const float4 a = tile[2 * p];
+                        const float4 b = (2 * p + 1 < np) ? tile[2 * p + 1]
+                                                          : make_float4(0.f, 0.f, qnan, qnan);
+                        tile[2 * p] = make_float4(a.x, b.x, a.y, b.y);
+                        tile[2 * p + 1] = make_float4(-a.z, -b.z, -a.w, -b.w);
+                    }
+                    __syncthreads();
+                }
             }
-            const int lo = tl * tile_pts;
-            const int np = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
-            int i = 0;
-            for (; i + 4 <= np; i += 4) {
-                float4 c[4];
+            if constexpr (PACKED) {
+                const int npair = (np + 1) >> 1;
+                int i = 0;
+                for (; i + 2 <= npair; i += 2) {
+                    float4 c[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    c[k] = tile[i + k];   // warp-uniform address: broadcast
+                    for (int k = 0; k < 4; ++k)
+                        c[k] = tile[2 * i + k];   // warp-uniform address: broadcast
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 2; ++k)
+#pragma unroll
+                        for (int j = 0; j < kRansacHpt; ++j)
+                            cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1], nthr2);
+                }
+                for (; i < npair; ++i) {
+                    const float4 c0 = tile[2 * i], c1 = tile[2 * i + 1];
 #pragma unroll
                     for (int j = 0; j < kRansacHpt; ++j)
-                        cnt[j] += ransac_inlier(h[j], c[k], thr2);
-            }
-            for (; i < np; ++i) {
-                const float4 c = tile[i];
+                        cnt[j] += ransac_inlier2(h2[j], c0, c1, nthr2);
+                }
+            } else {
+                int i = 0;
+                for (; i + 4 <= np; i += 4) {
+                    float4 c[4];
 #pragma unroll
-                for (int j = 0; j < kRansacHpt; ++j)
-                    cnt[j] += ransac_inlier(h[j], c, thr2);
+                    for (int k = 0; k < 4; ++k)
+                        c[k] = tile[i + k];   // warp-uniform address: broadcast
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int j = 0; j < kRansacHpt; ++j)
+                            cnt[j] += ransac_inlier(h[j], c[k], thr2);
+                }
+                for (; i < np; ++i) {
+                    const float4 c = tile[i];
+#pragma unroll
+                    for (int j = 0; j < kRansacHpt; ++j)
+                        cnt[j] += ransac_inlier(h[j], c, thr2);
+                }
             }
             if (n_tiles > 1) {   // stream the next tile (wraps for the next round)
                 __syncthreads();
