@@ -172,8 +172,9 @@ void sks_cuda_reset_launch_count(void);
  * for bench.py sweeps, not a backend switch: every variant is sm_100a CUDA. */
 int sks_cuda_set_variant(int variant);
 int sks_cuda_get_variant(void);
-/* Ring-kernel tuning: small_tile (0: 256 fp32 / 128 fp64 quadruples per tile,
- * 1: half of that), stages (2..16 shared-memory ring slots), ctas_per_sm
+/* Kernel tuning: small_tile bit 0 (ring kernel: 0 = 256 fp32 / 128 fp64 quadruples
+ * per tile, 1 = half of that), bit 1 (direct kernel: 1 = force 16-byte instead of
+ * 256-bit global accesses), stages (2..16 shared-memory ring slots), ctas_per_sm
  * (0 = as many as fit). */
 int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm);
 /* RANSAC kernel tuning: hypotheses carried per thread (2 or 4), scoring rounds

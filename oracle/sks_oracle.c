@@ -174,7 +174,7 @@ DEF_SYNTH(oracle_synth_quads_f64, double, u01_f64)
  *                 u = fma(h0,x,fma(h1,y,h2)); v = fma(h3,x,fma(h4,y,h5));
  *                 w = fma(h6,x,fma(h7,y,h8));
  *                 du = fma(X,w,-u); dv = fma(Y,w,-v);
- *                 e = fma(dv,dv,du*du); acc = fma(-(thr2*w), w, e);
+ *                 e = fma(dv,dv,du*du); acc = fma(-thr2, w*w, e);
  *                 inlier <=> acc < 0   (NaN is never an inlier)
  *   select    : key = count<<32 | (0xFFFFFFFF - hyp); best = max key
  *               (highest count, lowest hypothesis id on ties). */
@@ -191,7 +191,7 @@ uint32_t oracle_ransac_count_f32(const float *H, const float *corr, int32_t n_pt
         const float du = fmaf(X, w, -u);
         const float dv = fmaf(Y, w, -v);
         const float e = fmaf(dv, dv, du * du);
-        const float acc = fmaf(-(thr2 * w), w, e);
+        const float acc = fmaf(-thr2, w * w, e);
         cnt += (acc < 0.0f) ? 1u : 0u;
     }
     return cnt;

@@ -22,6 +22,7 @@ std::atomic<int> g_variant{0};        // 0 default, 1 direct, 2 ring
 std::atomic<int> g_tile_small{0};     // ring tile: 0 = 256/128 (f32/f64), 1 = 128/64
 std::atomic<int> g_stages{4};
 std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
+std::atomic<int> g_wide{1};           // direct kernel: 256-bit loads/stores when 32-byte aligned
 std::atomic<int> g_ransac_hpt{2};     // hypotheses per thread in the RANSAC kernel (2 or 4)
 std::atomic<int> g_ransac_packed{1};  // 1 = FFMA2/FMUL2 two-matches-per-instruction scoring (measured best)
 std::atomic<int> g_ransac_threads{256};
@@ -57,6 +58,7 @@ int device_info(DevInfo& out)
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 inline int finish_launch()
 {
@@ -126,12 +128,20 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
 
     int variant = g_variant.load();
     if (variant == 0) variant = 1;   // measured best on B200 (profiles/): direct > ring
-    constexpr int BIG = sizeof(T) == 4 ? 256 : 128;
+#ifndef SKS_DIRECT_TILE_F32
+#define SKS_DIRECT_TILE_F32 256
+#endif
+    constexpr int BIG = sizeof(T) == 4 ? SKS_DIRECT_TILE_F32 : 128;
     constexpr int SMALL = BIG / 2;
     if (variant == 1) {
         const int64_t grid = (n + BIG - 1) / BIG;
-        k_aos_direct<SOLVER, T, BIG><<<(unsigned)grid, BIG, 0, st>>>(src, tar, M, rp, H, degen, n,
-                                                                     normalize);
+        const bool wide = g_wide.load() && aligned32(H) && aligned32(tar) && (!src || aligned32(src));
+        if (wide)
+            k_aos_direct<SOLVER, T, BIG, true><<<(unsigned)grid, BIG, 0, st>>>(src, tar, M, rp, H,
+                                                                               degen, n, normalize);
+        else
+            k_aos_direct<SOLVER, T, BIG, false><<<(unsigned)grid, BIG, 0, st>>>(src, tar, M, rp, H,
+                                                                                degen, n, normalize);
         return finish_launch();
     }
     if (g_tile_small.load())
@@ -365,7 +375,8 @@ int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int pack
 int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm)
 {
     if (stages < 2 || stages > 16 || ctas_per_sm < 0) return SKS_ERR_INVALID_ARG;
-    g_tile_small.store(small_tile ? 1 : 0);
+    g_wide.store((small_tile & 2) ? 0 : 1);          // bit 1: force 16-byte accesses in the direct kernel
+    g_tile_small.store(small_tile & 1);
     g_stages.store(stages);
     g_ctas_per_sm.store(ctas_per_sm);
     return SKS_OK;

@@ -17,12 +17,29 @@ struct __align__(16) Chunk16 {
     uint32_t w[4];
 };
 
+// Experiment knobs (tools/hint_sweep.py builds the library with -DSKS_LD_HINT=n
+// -DSKS_ST_HINT=m); the defaults are the measured best.
+#ifndef SKS_LD_HINT
+#define SKS_LD_HINT 0
+#endif
+#ifndef SKS_ST_HINT
+#define SKS_ST_HINT 0
+#endif
+
 // read-only path, keep the line in L1 (two lanes-halves of one sector are read
 // by two consecutive instructions in the AoS direct kernel)
 __device__ __forceinline__ Chunk16 ldg_nc(const void* p)
 {
     Chunk16 c;
+#if SKS_LD_HINT == 1
+    asm volatile("ld.global.nc.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif SKS_LD_HINT == 2
+    asm volatile("ld.global.nc.L1::evict_last.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif SKS_LD_HINT == 3
+    asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+#else
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+#endif
                  : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3])
                  : "l"(p));
     return c;
@@ -38,10 +55,65 @@ __device__ __forceinline__ Chunk16 ldg_stream(const void* p)
 }
 __device__ __forceinline__ void stg_stream(void* p, const Chunk16& c)
 {
+#if SKS_ST_HINT == 1
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(c.w[0]),
+#elif SKS_ST_HINT == 2
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(c.w[0]),
+#elif SKS_ST_HINT == 3
+    asm volatile("st.global.L2::evict_first.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(c.w[0]),
+#else
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(c.w[0]),
+#endif
                  "r"(c.w[1]), "r"(c.w[2]), "r"(c.w[3])
                  : "memory");
 }
+// ---- 32-byte (256-bit) global accesses: new on sm_100 (SASS LDG.256 / STG.256).
+// One instruction moves a whole 32-byte sector per lane, which is exactly one
+// fp32 AoS quadruple: no half-sector re-reads, so nothing needs to stay in L1
+// (L1::no_allocate).  The hint variants below were swept on B200: loads are
+// insensitive (+-1 %), 256-bit STORES cost 4-10 % on the write-heavy solvers,
+// so results leave as 16-byte stores.
+struct __align__(32) Chunk32 {
+    uint32_t w[8];
+};
+// measured on B200 (profiles/r01_hint_sweep.log): no_allocate loads + 16-byte stores
+#ifndef SKS_WLD_HINT
+#define SKS_WLD_HINT 1
+#endif
+#ifndef SKS_WST_HINT
+#define SKS_WST_HINT 0
+#endif
+__device__ __forceinline__ Chunk32 ldg_stream32(const void* p)
+{
+    Chunk32 c;
+    asm volatile(
+#if SKS_WLD_HINT == 0
+        "ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif SKS_WLD_HINT == 1
+        "ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+        "ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+        : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]),
+          "=r"(c.w[6]), "=r"(c.w[7])
+        : "l"(p));
+    return c;
+}
+__device__ __forceinline__ void stg_stream32(void* p, const Chunk32& c)
+{
+    asm volatile(
+#if SKS_WST_HINT == 1
+        "st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+#elif SKS_WST_HINT == 2
+        "st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+#else
+        "st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+#endif
+        "r"(c.w[0]), "r"(c.w[1]), "r"(c.w[2]), "r"(c.w[3]), "r"(c.w[4]), "r"(c.w[5]), "r"(c.w[6]),
+        "r"(c.w[7])
+        : "memory");
+}
+
 __device__ __forceinline__ Chunk16 lds16(const void* p)
 {
     Chunk16 c;

@@ -9,7 +9,7 @@
 //     u = fma(h0,x,fma(h1,y,h2));  v = fma(h3,x,fma(h4,y,h5));
 //     w = fma(h6,x,fma(h7,y,h8));
 //     du = fma(X,w,-u); dv = fma(Y,w,-v); e = fma(dv,dv,du*du)
-//     acc = fma(-(thr2*w), w, e);  inlier <=> acc < 0
+//     acc = fma(-thr2, w*w, e);  inlier <=> acc < 0
 //   (division-free forward transfer error |proj(x) - X|^2 < thr2, both sides
 //   multiplied by w^2).  On the GPU "acc < 0" is read off the sign bit and added
 //   to the count with one integer instruction: acc is never -0 (e >= +0 and an
@@ -74,7 +74,7 @@ __device__ __forceinline__ uint32_t ransac_inlier(const float (&h)[9], const flo
     const float du = __fmaf_rn(c.z, w, -u);
     const float dv = __fmaf_rn(c.w, w, -v);
     const float e = __fmaf_rn(dv, dv, __fmul_rn(du, du));
-    const float acc = __fmaf_rn(-__fmul_rn(thr2, w), w, e);
+    const float acc = __fmaf_rn(-thr2, __fmul_rn(w, w), e);
     return __float_as_uint(acc) >> 31;
 }
 
@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t ransac_inlier(const float (&h)[9], const flo
 // pair layout the kernel rewrites the shared-memory tile into; h[k] = (h_k,h_k).
 // Bit-identical to two ransac_inlier calls: each half is an IEEE fused
 // multiply-add, u - X*w is the exact negation of X*w - u (its square is the
-// same), and (-thr2)*w is the exact negation of thr2*w.
+// same).
 __device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&h)[9], const float4 p0,
                                                    const float4 p1, const float2 nthr2)
 {
@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&h)[9], const f
     const float2 du = __ffma2_rn(nX, w, u);
     const float2 dv = __ffma2_rn(nY, w, v);
     const float2 e = __ffma2_rn(dv, dv, __fmul2_rn(du, du));
-    const float2 acc = __ffma2_rn(__fmul2_rn(nthr2, w), w, e);
+    const float2 acc = __ffma2_rn(nthr2, __fmul2_rn(w, w), e);
     return (__float_as_uint(acc.x) >> 31) + (__float_as_uint(acc.y) >> 31);
 }
 

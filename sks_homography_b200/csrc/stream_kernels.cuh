@@ -10,9 +10,11 @@
 //                 shared loads, and the 9-word results are transposed through
 //                 shared memory and leave as one bulk shared->global copy per
 //                 tile.  No register-staged global traffic at all.
-//   k_aos_direct  one tile per CTA; per-thread 16-byte read-only loads, results
-//                 transposed through shared memory into coalesced 16-byte
-//                 stores.  Simple comparison point / fallback for odd sizes.
+//   k_aos_direct  one tile per CTA; each thread pulls its own quadruple with
+//                 256-bit loads (sm_100's LDG.256: one full 32-byte sector per
+//                 lane) or, for pointers that are only 16-byte aligned, 16-byte
+//                 read-only loads; results are transposed through shared memory
+//                 into coalesced 256-bit / 16-byte streaming stores.
 //   k_soa         the reference GPU layout (GPU.cu:87-95,141-149): 16-byte
 //                 coalesced loads of 4 (fp32) / 2 (fp64) consecutive quadruples
 //                 per thread per coordinate plane, streaming cache hints.
@@ -89,6 +91,24 @@ __device__ __forceinline__ void load_quad_global(const T* p, T (&v)[8])
     }
 }
 
+// Same, with 256-bit loads (one per fp32 quadruple, two per fp64 quadruple).
+template <typename T>
+__device__ __forceinline__ void load_quad_global_wide(const T* p, T (&v)[8])
+{
+    constexpr int EPW = 32 / (int)sizeof(T), NW = 8 / EPW;   // elements per 32 bytes
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const Chunk32 c = ldg_stream32(p + j * EPW);
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) {
+            if constexpr (sizeof(T) == 4)
+                v[j * EPW + e] = __uint_as_float(c.w[e]);
+            else
+                v[j * EPW + e] = __hiloint2double((int)c.w[2 * e + 1], (int)c.w[2 * e]);
+        }
+    }
+}
+
 // One quadruple from an AoS shared-memory tile.  Thread `tid` owns bytes
 // [tid*8*sizeof(T), +8*sizeof(T)); a plain 16-byte read at that stride is a
 // 2-way (fp32) / 4-way (fp64) bank conflict, so each quarter-warp reads its
@@ -142,13 +162,14 @@ __device__ __forceinline__ void load_corner_aos(const T* M, int64_t i, T& mx, T&
 }
 
 // ------------------------------------------------------------ k_aos_direct
-template <int SOLVER, typename T, int TILE>
+// WIDE: 256-bit global loads and stores (needs 32-byte aligned base pointers).
+template <int SOLVER, typename T, int TILE, bool WIDE>
 __global__ void __launch_bounds__(TILE)
 k_aos_direct(const T* __restrict__ src, const T* __restrict__ tar, const T* __restrict__ M,
              RectParams<T> rp, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n,
              bool normalize)
 {
-    __shared__ __align__(16) T stage[TILE * 9];
+    __shared__ __align__(32) T stage[TILE * 9];
     const int tid = threadIdx.x;
     const int64_t q0 = (int64_t)blockIdx.x * TILE;
     const int64_t i = q0 + tid;
@@ -156,9 +177,15 @@ k_aos_direct(const T* __restrict__ src, const T* __restrict__ tar, const T* __re
     if (tid < cnt) {
         T s[8], t[8], h[9];
         T mx = rp.mx, my = rp.my;
-        if constexpr (SOLVER != SOLVER_RECT)
-            load_quad_global<T>(src + i * 8, s);
-        load_quad_global<T>(tar + i * 8, t);
+        if constexpr (WIDE) {
+            if constexpr (SOLVER != SOLVER_RECT)
+                load_quad_global_wide<T>(src + i * 8, s);
+            load_quad_global_wide<T>(tar + i * 8, t);
+        } else {
+            if constexpr (SOLVER != SOLVER_RECT)
+                load_quad_global<T>(src + i * 8, s);
+            load_quad_global<T>(tar + i * 8, t);
+        }
         if constexpr (SOLVER == SOLVER_RECT)
             if (M != nullptr)
                 load_corner_aos<T>(M, i, mx, my);
@@ -172,13 +199,30 @@ k_aos_direct(const T* __restrict__ src, const T* __restrict__ tar, const T* __re
     __syncthreads();
     // the tile's results are contiguous in H: cnt*9 elements from H + q0*9
     const int total = cnt * 9;
-    constexpr int EPC = ChunkTraits<T>::EPC;
-    const int nchunk = total / EPC;
     T* dst = H + q0 * 9;
-    for (int c = tid; c < nchunk; c += TILE)
-        stg_stream(dst + c * EPC, lds16(stage + c * EPC));
-    for (int e = nchunk * EPC + tid; e < total; e += TILE)
-        dst[e] = stage[e];
+    if constexpr (WIDE && SKS_WST_HINT != 0) {
+        constexpr int EPW = 32 / (int)sizeof(T);
+        const int nwide = total / EPW;
+        for (int c = tid; c < nwide; c += TILE) {
+            const Chunk16 lo = lds16(stage + c * EPW), hi = lds16(stage + c * EPW + EPW / 2);
+            Chunk32 w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w.w[k] = lo.w[k];
+                w.w[4 + k] = hi.w[k];
+            }
+            stg_stream32(dst + c * EPW, w);
+        }
+        for (int e = nwide * EPW + tid; e < total; e += TILE)
+            dst[e] = stage[e];
+    } else {
+        constexpr int EPC = ChunkTraits<T>::EPC;
+        const int nchunk = total / EPC;
+        for (int c = tid; c < nchunk; c += TILE)
+            stg_stream(dst + c * EPC, lds16(stage + c * EPC));
+        for (int e = nchunk * EPC + tid; e < total; e += TILE)
+            dst[e] = stage[e];
+    }
 }
 
 // -------------------------------------------------------------- k_aos_ring

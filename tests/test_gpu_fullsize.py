@@ -1,0 +1,90 @@
+"""BASELINE.json's FULL sizes on the GPU, checked through size-independent
+properties (the oracle cannot sweep 2^26..2^28 quadruples in a unit test):
+random slices against the oracle, agreement between independent kernels
+(direct / TMA ring / SoA) over the whole batch, and 64-bit offset coverage
+(9 * 2^28 elements > 2^31, where the reference's int indexing would overflow,
+GPU.cu:87-95,141-149)."""
+import numpy as np
+import pytest
+import torch
+
+from util import assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def api(sks, cuda):
+    from sks_homography_b200 import api as a
+    yield a
+    sks.c.sks_cuda_set_variant(0)
+    sks.c.sks_cuda_set_tuning(0, 4, 0)
+
+
+def check_slices(oracle, fn, src, tar, H, n, k=6, width=3000, seed=0):
+    rng = np.random.default_rng(seed)
+    starts = [0, n - width] + [int(x) for x in rng.integers(0, n - width, size=k)]
+    for b in starts:
+        s = None if src is None else src[b:b + width].cpu().numpy()
+        t = tar[b:b + width].cpu().numpy()
+        assert_same_bits(H[b:b + width].cpu().numpy(), fn(s, t), f"slice at {b}")
+
+
+def test_config2_aca_f32_2pow26(api, sks, oracle, cuda):
+    """configs[1]: batched ACA fp32, 2^26 quadruples, AoS, h33-normalised."""
+    n = 1 << 26
+    src, tar = api.synth_quads(n, seed=11, dist=0, dtype=torch.float32, device=cuda)
+    sks.c.sks_cuda_set_variant(1)
+    H1 = api.solve("aca", src, tar)
+    check_slices(oracle, lambda s, t: oracle.solve("aca", s, t), src, tar, H1, n)
+    # the generator itself at the far end of the index space
+    ws, wt = oracle.synth_quads(n - 1000, 1000, 11, 0, np.float32)
+    assert_same_bits(src[n - 1000:].cpu().numpy(), ws) and assert_same_bits(tar[n - 1000:].cpu().numpy(), wt)
+    # an independent kernel (TMA ring) must produce the same 2.25 GiB, bit for bit
+    sks.c.sks_cuda_set_variant(2)
+    H2 = api.solve("aca", src, tar)
+    assert torch.equal(H1.view(torch.int32), H2.view(torch.int32))
+    del H2
+    # every h33 is exactly 1, every quadruple of this distribution is well posed
+    assert bool((H1[:, 8] == 1.0).all()) and bool(torch.isfinite(H1).all())
+    # linearity-free but cheap global property: SKS agrees with ACA to fp32 conditioning
+    K = api.solve("sks", src, tar)
+    rel = (K - H1).abs().amax(1) / H1.abs().amax(1)
+    rel = rel[::61]                                   # torch.quantile caps its input size
+    assert float(rel.median()) < 1e-5 and float(rel.quantile(0.99)) < 1e-3
+
+
+def test_config3_rect_f32_2pow28_uses_64bit_offsets(api, oracle, cuda):
+    """configs[2]: TensorACA rect-to-quad, 2^28 quadruples (one GPU's worth of the
+    1-GPU point of the scaling series): 8 GiB in, 9 GiB out, offsets beyond 2^31."""
+    n = 1 << 28
+    _, tar = api.synth_quads(n, seed=5, dist=0, dtype=torch.float32, device=cuda)
+    H = api.aca_rect(tar, 128.0, 1.0, 15.0, 12.0)
+    assert H.numel() > 2**31
+    check_slices(oracle, lambda s, t: oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0), None, tar, H, n)
+    assert bool((H[:, 8] == 1.0).all())
+    del H
+    # SoA view of the same problem (planes of 2^28 elements, 1 GiB apart)
+    m = 1 << 26
+    t_soa = tar[:m].T.contiguous()
+    Hs = api.aca_rect(t_soa, 128.0, 1.0, 15.0, 12.0, layout="soa")
+    Ha = api.aca_rect(tar[:m], 128.0, 1.0, 15.0, 12.0)
+    assert torch.equal(Hs.T.contiguous().view(torch.int32), Ha.view(torch.int32))
+
+
+def test_config4_sks_f64_2pow25(api, sks, oracle, cuda):
+    """configs[3]: batched SKS fp64, 2^25 quadruples, accuracy tier."""
+    n = 1 << 25
+    src, tar = api.synth_quads(n, seed=41, dist=1, dtype=torch.float64, device=cuda)
+    H = api.solve("sks", src, tar)
+    check_slices(oracle, lambda s, t: oracle.solve("sks", s, t), src, tar, H, n)
+    A = api.solve("aca", src, tar)
+    rel = (A - H).abs().amax(1) / H.abs().amax(1)
+    rel = rel[::31]
+    assert float(rel.median()) < 1e-13 and float(rel.quantile(0.99)) < 1e-10
+    # 4-point reprojection of the fp64 result, on the device, far below 1e-4 px
+    Hm = H.view(n, 3, 3)
+    p = torch.cat([src.view(n, 4, 2), torch.ones(n, 4, 1, dtype=torch.float64, device=cuda)], dim=2)
+    q = torch.einsum("nij,nkj->nki", Hm, p)
+    err = ((q[..., :2] / q[..., 2:3]) - tar.view(n, 4, 2)).norm(dim=2).amax(1)
+    assert float(err.max()) < 1e-6

@@ -14,8 +14,8 @@ from util import assert_same_bits, reproject_error
 pytestmark = pytest.mark.gpu
 
 TDT = {np.float32: torch.float32, np.float64: torch.float64}
-VARIANTS = {"direct": (1, 0, 4, 0), "ring": (2, 0, 4, 0), "ring_small_3": (2, 1, 3, 0),
-            "ring_1cta_2": (2, 0, 2, 1)}
+VARIANTS = {"direct": (1, 0, 4, 0), "direct_16B": (1, 2, 4, 0), "ring": (2, 0, 4, 0),
+            "ring_small_3": (2, 1, 3, 0), "ring_1cta_2": (2, 0, 2, 1)}
 
 
 @pytest.fixture
@@ -51,7 +51,7 @@ def test_aos_bit_exact(api, sks, oracle, cuda, solver, dtype, variant):
         assert np.array_equal(flag.cpu().numpy(), oracle.degenerate(want, normalize))
 
 
-@pytest.mark.parametrize("variant", ["direct", "ring"])
+@pytest.mark.parametrize("variant", ["direct", "direct_16B", "ring"])
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 31, 255, 256, 257, 511, 1000, 4099])
 def test_ragged_sizes(api, sks, oracle, cuda, n, variant):
     set_variant(sks, variant)
@@ -210,6 +210,21 @@ def test_fp64_accuracy_tier(api, oracle, cuda):
     assert np.percentile(rel, 99) < 1e-10
     assert np.percentile(reproject_error(k, s, t), 99) < 1e-9
     assert reproject_error(k, s, t).max() < 1e-4
+
+
+def test_16_byte_aligned_buffers_take_the_narrow_path(api, oracle, cuda):
+    """Base pointers that are 16- but not 32-byte aligned cannot use LDG.256."""
+    n = 5000
+    s, t = oracle.synth_quads(0, n, 8, 1, np.float32)
+    pad = torch.zeros(n * 8 + 4, dtype=torch.float32, device=cuda)
+    pad2 = torch.zeros(n * 8 + 4, dtype=torch.float32, device=cuda)
+    out = torch.zeros(n * 9 + 4, dtype=torch.float32, device=cuda)
+    sv, tv, ov = pad[4:].view(n, 8), pad2[4:].view(n, 8), out[4:].view(n, 9)
+    assert sv.data_ptr() % 32 == 16
+    sv.copy_(torch.from_numpy(s)); tv.copy_(torch.from_numpy(t))
+    api.solve("aca", sv, tv, result=ov)
+    assert_same_bits(ov.cpu().numpy(), oracle.solve("aca", s, t), "16-byte aligned views")
+    assert float(out[:4].abs().sum()) == 0.0
 
 
 def test_unaligned_pointer_is_rejected(api, sks, cuda):
