@@ -1,7 +1,7 @@
 // Host-pointer entry points: the drop-in for the reference's C++ call sites,
 // which hold plain host arrays (CPU/main.cpp:47-58,87-114).  A batch is cut
-// into chunks that flow through a ring of device buffers on independent
-// streams, so the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy
+// into 2^18-quadruple chunks that flow through a 4-slot ring of device buffers on
+// independent streams, so the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy
 // of chunk c-1 overlap (the path is PCIe-bound: 100 B cross the bus per
 // homography against ~100 flops of work).  Pinned caller buffers are copied
 // directly; pageable ones are staged through an internal pinned ring with a
@@ -20,8 +20,10 @@
 
 namespace {
 
-constexpr int kRing = 3;
-constexpr int64_t kChunkBytesIn = 32ll << 20;   // per input array per chunk
+constexpr int kRing = 4;
+// per input array per chunk: small enough that filling and draining the pipeline costs
+// ~1 % of a 2^25-quadruple batch, large enough for full-rate PCIe DMA
+constexpr int64_t kChunkBytesIn = 8ll << 20;
 
 struct Slot {
     void* d_in[3] = {nullptr, nullptr, nullptr};   // src, tar, M

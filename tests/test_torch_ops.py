@@ -1,0 +1,35 @@
+"""torch.library binding: registration + shape propagation on CPU (fake tensors),
+numerics on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from util import assert_same_bits
+
+
+def test_ops_are_registered_and_trace_with_fake_tensors(sks):
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import sks_homography_b200.torch_ops  # noqa: F401
+    assert hasattr(torch.ops.sks_b200, "solve") and hasattr(torch.ops.sks_b200, "aca_rect")
+    with FakeTensorMode():
+        s = torch.empty(100, 4, 2)
+        t = torch.empty(100, 4, 2)
+        H = torch.ops.sks_b200.solve(s, t, "aca", True)
+        assert H.shape == (100, 9) and H.dtype == torch.float32
+        R = torch.ops.sks_b200.aca_rect(torch.empty(7, 8, dtype=torch.float64), None, 1.0, 2.0, 50.0, 1.25, False)
+        assert R.shape == (7, 9) and R.dtype == torch.float64
+        Hb, cnt, hyp = torch.ops.sks_b200.ransac(torch.empty(5, 64, 4), 128, 1, 4.0)
+        assert Hb.shape == (5, 9) and cnt.shape == (5,) and hyp.dtype == torch.int64
+
+
+@pytest.mark.gpu
+def test_ops_match_oracle_on_gpu(sks, oracle, cuda):
+    import sks_homography_b200.torch_ops  # noqa: F401
+    s, t = oracle.synth_quads(0, 10_000, 3, 1, np.float32)
+    H = torch.ops.sks_b200.solve(torch.from_numpy(s).to(cuda), torch.from_numpy(t).to(cuda), "sks", True)
+    assert_same_bits(H.cpu().numpy(), oracle.solve("sks", s, t), "torch op sks")
+    R = torch.ops.sks_b200.aca_rect(torch.from_numpy(t).to(cuda), None, 15.0, 12.0, 128.0, 1.0, True)
+    assert_same_bits(R.cpu().numpy(), oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0), "torch op rect")
+    torch.library.opcheck(torch.ops.sks_b200.solve.default,
+                          (torch.from_numpy(s[:64]).to(cuda), torch.from_numpy(t[:64]).to(cuda), "aca", False),
+                          test_utils=("test_schema", "test_faketensor"))
