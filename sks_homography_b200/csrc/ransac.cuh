@@ -32,6 +32,14 @@
 #include "solvers.cuh"
 #include "synth.cuh"
 
+// inner-loop shape of the packed scorer (swept in tools/ransac_sweep.py)
+#ifndef SKS_RANSAC_UNROLL
+#define SKS_RANSAC_UNROLL 2      // match PAIRS per unrolled iteration
+#endif
+#ifndef SKS_RANSAC_HYP_MAJOR
+#define SKS_RANSAC_HYP_MAJOR 0
+#endif
+
 namespace sksb {
 
 constexpr int kRansacMaxTilePts = 8192;    // 128 KiB of shared memory at most
@@ -192,16 +200,24 @@ k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
             if constexpr (PACKED) {
                 const int npair = (np + 1) >> 1;
                 int i = 0;
-                for (; i + 2 <= npair; i += 2) {
-                    float4 c[4];
+                for (; i + SKS_RANSAC_UNROLL <= npair; i += SKS_RANSAC_UNROLL) {
+                    float4 c[2 * SKS_RANSAC_UNROLL];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 2 * SKS_RANSAC_UNROLL; ++k)
                         c[k] = tile[2 * i + k];   // warp-uniform address: broadcast
+#if SKS_RANSAC_HYP_MAJOR
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
+                    for (int j = 0; j < kRansacHpt; ++j)
+#pragma unroll
+                        for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
+                            cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1], nthr2);
+#else
+#pragma unroll
+                    for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
 #pragma unroll
                         for (int j = 0; j < kRansacHpt; ++j)
                             cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1], nthr2);
+#endif
                 }
                 for (; i < npair; ++i) {
                     const float4 c0 = tile[2 * i], c1 = tile[2 * i + 1];

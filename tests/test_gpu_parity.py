@@ -227,6 +227,30 @@ def test_16_byte_aligned_buffers_take_the_narrow_path(api, oracle, cuda):
     assert float(out[:4].abs().sum()) == 0.0
 
 
+def test_launch_is_cuda_graph_capturable(api, oracle, cuda):
+    """The device-pointer entry points only enqueue (no sync, no allocation), so a
+    launch-bound loop of small solves can be captured once and replayed."""
+    n = 777
+    s, t = oracle.synth_quads(0, n, 19, 1, np.float32)
+    ds, dt_ = dev(s, cuda), dev(t, cuda)
+    outs = [torch.zeros((n, 9), dtype=torch.float32, device=cuda) for _ in range(4)]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        api.solve("aca", ds, dt_, result=outs[0])          # warm-up outside capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for k, solver in enumerate(("aca", "sks", "aca", "sks")):
+                api.solve(solver, ds, dt_, result=outs[k], normalize=(k < 2))
+        for o in outs:
+            o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+    assert_same_bits(outs[0].cpu().numpy(), oracle.solve("aca", s, t), "graph aca")
+    assert_same_bits(outs[1].cpu().numpy(), oracle.solve("sks", s, t), "graph sks")
+    assert_same_bits(outs[3].cpu().numpy(), oracle.solve("sks", s, t, normalize=False), "graph sks raw")
+
+
 def test_unaligned_pointer_is_rejected(api, sks, cuda):
     buf = torch.zeros(64, dtype=torch.float32, device=cuda)
     p = buf.data_ptr()
