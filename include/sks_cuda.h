@@ -104,6 +104,14 @@ int sks_host_aca_rect_f32(const float *tar, const float *M, float mx, float my, 
                           float ratio, float *H, int64_t n, int flags);
 int sks_host_aca_rect_f64(const double *tar, const double *M, double mx, double my,
                           double width, double ratio, double *H, int64_t n, int flags);
+/* In-process multi-GPU driver for the host-pointer entry points: shard every batch
+ * contiguously over `count` GPUs (devices 0..count-1; 0 = all visible; default 1 =
+ * the current device only), one host thread and one PCIe link per GPU, no
+ * inter-GPU traffic. */
+int sks_host_set_device_count(int count);
+/* Pipeline granularity of the host-pointer path: bytes of ONE input array per chunk
+ * (upper bound, default 64 MiB; 64 KiB .. 1 GiB; batches are cut into ~8 chunks). */
+int sks_host_set_chunk_bytes(int64_t bytes_per_input_array);
 /* pinned host allocation helpers for callers that want the zero-staging path */
 int sks_host_alloc_pinned(void **ptr, int64_t bytes);
 int sks_host_free_pinned(void *ptr);

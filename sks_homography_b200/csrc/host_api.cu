@@ -1,13 +1,14 @@
 // Host-pointer entry points: the drop-in for the reference's C++ call sites,
 // which hold plain host arrays (CPU/main.cpp:47-58,87-114).  A batch is cut
-// into 2^18-quadruple chunks that flow through a 4-slot ring of device buffers on
-// independent streams, so the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy
+// into chunks (up to 64 MiB per input array) that flow through a 4-slot ring of
+// device buffers on independent streams, so the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy
 // of chunk c-1 overlap (the path is PCIe-bound: 100 B cross the bus per
 // homography against ~100 flops of work).  Pinned caller buffers are copied
 // directly; pageable ones are staged through an internal pinned ring with a
 // multi-threaded memcpy.  The layer sits strictly above the device-pointer
 // C ABI: it calls sks_cuda_* like any other client.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -21,9 +22,15 @@
 namespace {
 
 constexpr int kRing = 4;
+}  // namespace
+#include <atomic>
+namespace {
 // per input array per chunk: small enough that filling and draining the pipeline costs
 // ~1 % of a 2^25-quadruple batch, large enough for full-rate PCIe DMA
-constexpr int64_t kChunkBytesIn = 8ll << 20;
+// Upper bound of one input array per chunk.  Measured on B200 / PCIe Gen5
+// (tools/host_chunk_sweep.py): 1 MiB 36.7, 8 MiB 44.5, 32 MiB 49.2, 64 MiB 49.8 GB/s
+// H2D -- large DMAs win, so chunks are as large as still leaves ~8 of them to overlap.
+std::atomic<int64_t> g_chunk_bytes{64ll << 20};
 
 struct Slot {
     void* d_in[3] = {nullptr, nullptr, nullptr};   // src, tar, M
@@ -37,13 +44,15 @@ struct Slot {
 
 struct HostCtx {
     int device = -1;
+    std::mutex mu;                     // one batch at a time per device
     int64_t cap_in = 0, cap_out = 0;   // bytes per device buffer
     bool staged_in = false, staged_out = false;
     Slot slot[kRing];
 };
 
-std::mutex g_mu;
+std::mutex g_mu;                       // guards g_ctx and context (re)allocation
 std::vector<HostCtx*> g_ctx;
+std::atomic<int> g_host_devices{1};    // GPUs a host-pointer batch is sharded over (1 = current only)
 
 #define CK(x)                                  \
     do {                                       \
@@ -70,14 +79,10 @@ void free_ctx(HostCtx* c)
     delete c;
 }
 
-int get_ctx(int64_t need_in, int64_t need_out, bool stage_in, bool stage_out, HostCtx** out)
+int get_ctx(int dev, int64_t need_in, int64_t need_out, bool stage_in, bool stage_out,
+            HostCtx** out)
 {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SKS_ERR_NO_DEVICE : (int)e;
-    }
+    std::lock_guard<std::mutex> table(g_mu);
     HostCtx* c = nullptr;
     for (HostCtx* x : g_ctx)
         if (x->device == dev) c = x;
@@ -160,24 +165,21 @@ void parallel_copy(void* dst, const void* src, size_t bytes)
 // per quadruple; out is 9 elements per quadruple; `launch` enqueues the solver
 // for `cnt` quadruples on device buffers.
 template <typename T, typename Launch>
-int run_pipeline(const T* const* in, const int* in_elems, int n_in, T* out, int64_t n, Launch launch)
+int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T* out, int64_t n,
+                  Launch launch)
 {
-    if (n < 0 || out == nullptr) return SKS_ERR_INVALID_ARG;
-    for (int k = 0; k < n_in; ++k)
-        if (in[k] == nullptr) return SKS_ERR_INVALID_ARG;
-    if (n == 0) {
-        int cnt = 0;
-        return sks_cuda_device_count(&cnt);
-    }
-    std::lock_guard<std::mutex> lk(g_mu);
-    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, kChunkBytesIn / (8 * (int64_t)sizeof(T))));
+    CK(cudaSetDevice(dev));
+    const int64_t cap = g_chunk_bytes.load() / (8 * (int64_t)sizeof(T));
+    const int64_t floor_q = std::min<int64_t>(cap, (8ll << 20) / (8 * (int64_t)sizeof(T)));
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, std::min(cap, std::max(floor_q, (n + 7) / 8))));
     bool stage_in = false;
     for (int k = 0; k < n_in; ++k) stage_in = stage_in || !is_pinned(in[k]);
     const bool stage_out = !is_pinned(out);
     HostCtx* c = nullptr;
-    if (int rc = get_ctx(chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T), stage_in,
+    if (int rc = get_ctx(dev, chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T), stage_in,
                          stage_out, &c))
         return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
 
     auto drain = [&](Slot& s) -> int {   // finish the chunk this slot last produced
         if (s.pending_off < 0) return SKS_OK;
@@ -216,6 +218,46 @@ int run_pipeline(const T* const* in, const int* in_elems, int n_in, T* out, int6
         if (rc == SKS_OK) rc = r2;
     }
     return rc;
+}
+
+// Generic pipeline.  in[k] (k < n_in) are host arrays of in_elems[k] elements
+// per quadruple; out is 9 elements per quadruple; `launch` enqueues the solver
+// for `cnt` quadruples on device buffers.  With sks_host_set_device_count(g > 1)
+// the batch is cut into g contiguous shards, one host thread
+// and one PCIe link per GPU, no inter-GPU traffic.
+template <typename T, typename Launch>
+int run_pipeline(const T* const* in, const int* in_elems, int n_in, T* out, int64_t n, Launch launch)
+{
+    if (n < 0 || (n > 0 && out == nullptr)) return SKS_ERR_INVALID_ARG;
+    for (int k = 0; k < n_in; ++k)
+        if (n > 0 && in[k] == nullptr) return SKS_ERR_INVALID_ARG;
+    int visible = 0;
+    if (int rc = sks_cuda_device_count(&visible)) return rc;
+    if (visible <= 0) return SKS_ERR_NO_DEVICE;
+    if (n == 0) return SKS_OK;
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    int want = g_host_devices.load();
+    if (want <= 0 || want > visible) want = visible;
+    const int g = (int)std::min<int64_t>(want, std::max<int64_t>(1, n / (1 << 16)));
+    if (g <= 1) return run_on_device<T>(cur, in, in_elems, n_in, out, n, launch);
+
+    std::vector<int> rcs(g, SKS_OK);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < g; ++d) {
+        int64_t begin = 0, count = 0;
+        sks_cuda_shard_range(n, d, g, &begin, &count);
+        workers.emplace_back([=, &rcs] {
+            const T* sub[3] = {nullptr, nullptr, nullptr};
+            for (int k = 0; k < n_in; ++k) sub[k] = in[k] + begin * in_elems[k];
+            rcs[d] = run_on_device<T>(d, sub, in_elems, n_in, out + begin * 9, count, launch);
+        });
+    }
+    for (auto& w : workers) w.join();
+    cudaSetDevice(cur);
+    for (int rc : rcs)
+        if (rc != SKS_OK) return rc;
+    return SKS_OK;
 }
 
 template <typename T, typename Fn>
@@ -286,6 +328,20 @@ int sks_host_free_pinned(void* ptr)
 {
     cudaError_t e = cudaFreeHost(ptr);
     return e == cudaSuccess ? SKS_OK : (int)e;
+}
+
+int sks_host_set_chunk_bytes(int64_t bytes_per_input_array)
+{
+    if (bytes_per_input_array < (64 << 10) || bytes_per_input_array > (1ll << 30)) return SKS_ERR_INVALID_ARG;
+    g_chunk_bytes.store(bytes_per_input_array);
+    return SKS_OK;
+}
+
+int sks_host_set_device_count(int count)
+{
+    if (count < 0) return SKS_ERR_INVALID_ARG;
+    g_host_devices.store(count);       // 0 = every visible GPU
+    return SKS_OK;
 }
 
 int sks_cuda_shutdown(void)

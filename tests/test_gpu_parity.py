@@ -256,3 +256,21 @@ def test_unaligned_pointer_is_rejected(api, sks, cuda):
     p = buf.data_ptr()
     st = sks.c.sks_cuda_aca_f32(p + 4, p, p, 1, 0, 0, 1, None, None)
     assert st == -2
+
+
+def test_in_process_multi_gpu_host_driver(api, sks, oracle, cuda):
+    """sks_host_set_device_count: a host-pointer batch sharded over every visible GPU
+    by the library itself gives the same bytes as one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (covered by the gloo test and tools/gpu_multi.sh otherwise)")
+    n = (1 << 21) + 77
+    s, t = oracle.synth_quads(0, n, 29, 1, np.float32)
+    want = oracle.solve("sks", s, t)
+    try:
+        assert sks.c.sks_host_set_device_count(0) == 0          # all visible GPUs
+        H = api.solve("sks", torch.from_numpy(s).pin_memory(), torch.from_numpy(t).pin_memory())
+        assert_same_bits(H.numpy(), want, "multi-GPU host path, pinned")
+        H = api.solve("sks", torch.from_numpy(s), torch.from_numpy(t))
+        assert_same_bits(H.numpy(), want, "multi-GPU host path, pageable")
+    finally:
+        sks.c.sks_host_set_device_count(1)
