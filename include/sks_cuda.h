@@ -89,6 +89,17 @@ int sks_cuda_aca_rect_f64(const double *tar, const double *M, double mx, double 
                           double width, double ratio, double *H, int64_t n, int layout,
                           int64_t ld, int flags, uint8_t *degenerate, void *stream);
 
+/* Same solver on the reference's torch tensor convention (PY.py:24-37,286-302):
+ * tar34 / src34 are [n][3][4] homogeneous point matrices (rows x, y, 1; columns
+ * TL,TR,BL,BR), read in place without a transposing copy; src34 (nullable)
+ * supplies the per-sample corner src34[i][0..1][0] as PY.py:302 does.  H is AoS. */
+int sks_cuda_aca_rect_planar_f32(const float *tar34, const float *src34, float mx, float my,
+                                 float width, float ratio, float *H, int64_t n, int flags,
+                                 uint8_t *degenerate, void *stream);
+int sks_cuda_aca_rect_planar_f64(const double *tar34, const double *src34, double mx, double my,
+                                 double width, double ratio, double *H, int64_t n, int flags,
+                                 uint8_t *degenerate, void *stream);
+
 /* ---- host-pointer entry points (what the reference's C++ callers hold) ---- */
 /* Drop-in for the loop `for (k...) sks::runKernel_*(src, tar, result)` of
  * CPU/main.cpp:87-114 over n quadruples: AoS host buffers in, AoS host buffer

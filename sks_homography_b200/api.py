@@ -157,6 +157,16 @@ def TensorACA_rect(bs: int, src: torch.Tensor, tar: torch.Tensor, scale, div) ->
     div = width/height of the shared source square; the per-sample corner is
     src[:, 0:2, 0] (PY.py:302).  Returns the un-normalised H [bs,3,3] that the
     reference computes and discards."""
+    if tar.is_cuda and tar.dtype in _SUFFIX and src.dtype == tar.dtype and tar.shape[1:] == (3, 4):
+        # read the [bs,3,4] tensors in place (no transposing copy)
+        L = lib()
+        tar, src = tar.contiguous(), src.contiguous()
+        H = torch.empty((bs, 3, 3), dtype=tar.dtype, device=tar.device)
+        with torch.cuda.device(tar.device):
+            fn = getattr(L.c, f"sks_cuda_aca_rect_planar_{_SUFFIX[tar.dtype]}")
+            L.check(fn(_ptr(tar), _ptr(src), 0.0, 0.0, float(scale), float(div), _ptr(H), bs, 0, None,
+                       _stream_ptr(tar)), "sks_cuda_aca_rect_planar")
+        return H
     tarq = tar[:, :2, :].transpose(1, 2).reshape(bs, 8)
     M = src[:, :2, 0].contiguous()
     H = aca_rect(tarq, float(scale), float(div), M=M, normalize=False)

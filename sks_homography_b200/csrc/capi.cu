@@ -150,6 +150,23 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
 }
 
 template <typename T>
+int launch_rect_planar(const T* tar34, const T* src34, RectParams<T> rp, T* H, int64_t n, int flags,
+                       uint8_t* degen, void* stream)
+{
+    if (n < 0 || (flags & ~SKS_FLAG_NORMALIZE)) return SKS_ERR_INVALID_ARG;
+    if (n > 0 && (tar34 == nullptr || H == nullptr)) return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n == 0) return SKS_OK;
+    if (!aligned16(tar34) || !aligned16(H) || (src34 && !aligned16(src34))) return SKS_ERR_UNALIGNED;
+    constexpr int TILE = sizeof(T) == 4 ? 256 : 128;
+    const int64_t grid = (n + TILE - 1) / TILE;
+    k_rect_planar34<T, TILE><<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(
+        tar34, src34, rp, H, degen, n, (flags & SKS_FLAG_NORMALIZE) != 0);
+    return finish_launch();
+}
+
+template <typename T>
 int launch_synth_quads(T* src, T* tar, int64_t begin, int64_t count, uint64_t seed, int dist,
                        int layout, int64_t ld, void* stream)
 {
@@ -235,6 +252,21 @@ SKS_DEFINE_GENERAL(sks_cuda_sks_f64, SOLVER_SKS, double)
 SKS_DEFINE_RECT(sks_cuda_aca_rect_f32, float)
 SKS_DEFINE_RECT(sks_cuda_aca_rect_f64, double)
 
+int sks_cuda_aca_rect_planar_f32(const float* tar34, const float* src34, float mx, float my,
+                                 float width, float ratio, float* H, int64_t n, int flags,
+                                 uint8_t* degenerate, void* stream)
+{
+    return launch_rect_planar<float>(tar34, src34, RectParams<float>{mx, my, width, ratio}, H, n, flags,
+                                     degenerate, stream);
+}
+int sks_cuda_aca_rect_planar_f64(const double* tar34, const double* src34, double mx, double my,
+                                 double width, double ratio, double* H, int64_t n, int flags,
+                                 uint8_t* degenerate, void* stream)
+{
+    return launch_rect_planar<double>(tar34, src34, RectParams<double>{mx, my, width, ratio}, H, n,
+                                      flags, degenerate, stream);
+}
+
 int sks_cuda_gather_samples_f32(const float* pool, uint32_t pool_size, const uint32_t* rand4,
                                 uint64_t seed, float* src, float* tar, int64_t n, int layout,
                                 int64_t ld, void* stream)
@@ -255,8 +287,7 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
 {
     if (corr == nullptr || best_key == nullptr || n_pairs < 0 || n_pts <= 0)
         return SKS_ERR_INVALID_ARG;
-    if (n_pairs > 65535) return SKS_ERR_INVALID_ARG;   // grid.y; shard larger batches
-    if (samples != nullptr && (hyp_stride < hyp_begin + hyp_count || !aligned16(samples)))
+    if (samples != nullptr && ((uint64_t)hyp_stride < (uint64_t)hyp_begin + hyp_count || !aligned16(samples)))
         return SKS_ERR_INVALID_ARG;
     if (!aligned16(corr)) return SKS_ERR_UNALIGNED;
     DevInfo dev;
@@ -267,7 +298,7 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
     const int hpt = g_ransac_hpt.load();
     const bool packed = g_ransac_packed.load() != 0;
     const int threads = g_ransac_threads.load();
-    using Kern = void (*)(const float4*, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
+    using Kern = void (*)(const float4*, int64_t, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
                           uint32_t, uint32_t, uint64_t, float, unsigned long long*);
     Kern kern;
     if (threads == 512)
@@ -289,11 +320,17 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
            (int64_t)((hyp_count + chunk - 1) / chunk) * n_pairs < (int64_t)dev.sms * 8)
         chunk -= round;
     const unsigned chunks = (hyp_count + chunk - 1) / chunk;
-    dim3 grid(chunks, (unsigned)n_pairs);
-    kern<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4*>(corr), n_pts, tile_pts, samples, hyp_stride, hyp_begin,
-        hyp_count, chunk, seed_key(seed), thr2, best_key);
-    return finish_launch();
+    // grid.y is limited to 65535: larger batches go out in blocks of pairs; the kernel
+    // takes its pair id from pair_base + blockIdx.y so sampling does not depend on blocking
+    for (int64_t p0 = 0; p0 < n_pairs; p0 += 65535) {
+        const int64_t np = n_pairs - p0 < 65535 ? n_pairs - p0 : 65535;
+        dim3 grid(chunks, (unsigned)np);
+        kern<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(corr), p0, n_pts, tile_pts, samples, hyp_stride, hyp_begin,
+            hyp_count, chunk, seed_key(seed), thr2, best_key);
+        if (int rc = finish_launch()) return rc;
+    }
+    return SKS_OK;
 }
 
 int sks_cuda_ransac_finalize_f32(const float* corr, int64_t n_pairs, int32_t n_pts,

@@ -186,7 +186,7 @@ __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_
 // per instruction with FFMA2/FMUL2 (the tile is re-laid out in pairs on arrival).
 template <int kRansacHpt, bool PACKED, int kRansacThreads>
 __global__ void __launch_bounds__(kRansacThreads)
-k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
+k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, int32_t tile_pts,
              const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
              uint32_t hyp_count, uint32_t chunk_size, uint64_t key, float thr2,
              unsigned long long* __restrict__ best_key)
@@ -197,7 +197,7 @@ k_ransac_aca(const float4* __restrict__ corr, int32_t n_pts, int32_t tile_pts,
     __shared__ unsigned long long warp_best[kRansacThreads / 32];
 
     const int tid = threadIdx.x;
-    const int64_t pair = blockIdx.y;
+    const int64_t pair = pair_base + blockIdx.y;
     const float4* corr_pair = corr + (size_t)pair * n_pts;
     const uint32_t c_lo = blockIdx.x * chunk_size;
     if (c_lo >= hyp_count)

@@ -161,6 +161,39 @@ __device__ __forceinline__ void load_corner_aos(const T* M, int64_t i, T& mx, T&
     }
 }
 
+// Coalesced write-out of one tile: the 9*cnt results staged in shared memory are
+// contiguous in H (AoS), so they leave as 16-byte (or 256-bit) streaming stores.
+template <typename T, int TILE, bool WIDE>
+__device__ __forceinline__ void store_tile(const T* stage, T* __restrict__ H, int64_t q0, int cnt,
+                                           int tid)
+{
+    const int total = cnt * 9;
+    T* dst = H + q0 * 9;
+    if constexpr (WIDE && SKS_WST_HINT != 0) {
+        constexpr int EPW = 32 / (int)sizeof(T);
+        const int nwide = total / EPW;
+        for (int c = tid; c < nwide; c += TILE) {
+            const Chunk16 lo = lds16(stage + c * EPW), hi = lds16(stage + c * EPW + EPW / 2);
+            Chunk32 w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w.w[k] = lo.w[k];
+                w.w[4 + k] = hi.w[k];
+            }
+            stg_stream32(dst + c * EPW, w);
+        }
+        for (int e = nwide * EPW + tid; e < total; e += TILE)
+            dst[e] = stage[e];
+    } else {
+        constexpr int EPC = ChunkTraits<T>::EPC;
+        const int nchunk = total / EPC;
+        for (int c = tid; c < nchunk; c += TILE)
+            stg_stream(dst + c * EPC, lds16(stage + c * EPC));
+        for (int e = nchunk * EPC + tid; e < total; e += TILE)
+            dst[e] = stage[e];
+    }
+}
+
 // ------------------------------------------------------------ k_aos_direct
 // WIDE: 256-bit global loads and stores (needs 32-byte aligned base pointers).
 template <int SOLVER, typename T, int TILE, bool WIDE>
@@ -197,32 +230,57 @@ k_aos_direct(const T* __restrict__ src, const T* __restrict__ tar, const T* __re
             degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
     }
     __syncthreads();
-    // the tile's results are contiguous in H: cnt*9 elements from H + q0*9
-    const int total = cnt * 9;
-    T* dst = H + q0 * 9;
-    if constexpr (WIDE && SKS_WST_HINT != 0) {
-        constexpr int EPW = 32 / (int)sizeof(T);
-        const int nwide = total / EPW;
-        for (int c = tid; c < nwide; c += TILE) {
-            const Chunk16 lo = lds16(stage + c * EPW), hi = lds16(stage + c * EPW + EPW / 2);
-            Chunk32 w;
+    store_tile<T, TILE, WIDE>(stage, H, q0, cnt, tid);
+}
+
+// --------------------------------------------------------- k_rect_planar34
+// ACA-rect on the reference's torch tensor convention (PY.py:24-37, :286-302):
+// tar34 / src34 are [n][3][4] homogeneous (rows x, y, 1; columns TL,TR,BL,BR).
+// Each thread reads the x row and the y row of its sample (two 16-byte loads at
+// a 48-byte stride, fp64: four at 96); the constant row of ones is never used.
+// The per-sample rectangle corner is src34[i][0..1][0] (PY.py:302).
+template <typename T, int TILE>
+__global__ void __launch_bounds__(TILE)
+k_rect_planar34(const T* __restrict__ tar34, const T* __restrict__ src34, RectParams<T> rp,
+                T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, bool normalize)
+{
+    __shared__ __align__(32) T stage[TILE * 9];
+    constexpr int EPC = ChunkTraits<T>::EPC, NC = 4 / EPC;   // 16-byte chunks per row
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.x * TILE;
+    const int64_t i = q0 + tid;
+    const int cnt = (int)((n - q0) < (int64_t)TILE ? (n - q0) : (int64_t)TILE);
+    if (tid < cnt) {
+        T xr[4], yr[4], t[8], s[8], h[9];
+        const T* base = tar34 + i * 12;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                w.w[k] = lo.w[k];
-                w.w[4 + k] = hi.w[k];
+        for (int j = 0; j < NC; ++j) {
+            const Chunk16 cx = ldg_nc(base + j * EPC), cy = ldg_nc(base + 4 + j * EPC);
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) {
+                xr[j * EPC + e] = ChunkTraits<T>::get(cx, e);
+                yr[j * EPC + e] = ChunkTraits<T>::get(cy, e);
             }
-            stg_stream32(dst + c * EPW, w);
         }
-        for (int e = nwide * EPW + tid; e < total; e += TILE)
-            dst[e] = stage[e];
-    } else {
-        constexpr int EPC = ChunkTraits<T>::EPC;
-        const int nchunk = total / EPC;
-        for (int c = tid; c < nchunk; c += TILE)
-            stg_stream(dst + c * EPC, lds16(stage + c * EPC));
-        for (int e = nchunk * EPC + tid; e < total; e += TILE)
-            dst[e] = stage[e];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            t[2 * k] = xr[k];
+            t[2 * k + 1] = yr[k];
+        }
+        T mx = rp.mx, my = rp.my;
+        if (src34 != nullptr) {
+            mx = __ldg(src34 + i * 12);
+            my = __ldg(src34 + i * 12 + 4);
+        }
+        solve_quad<SOLVER_RECT, T>(s, t, mx, my, rp, h, normalize);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            stage[tid * 9 + k] = h[k];
+        if (degen != nullptr)
+            degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
     }
+    __syncthreads();
+    store_tile<T, TILE, false>(stage, H, q0, cnt, tid);
 }
 
 // -------------------------------------------------------------- k_aos_ring

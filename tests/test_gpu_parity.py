@@ -274,3 +274,32 @@ def test_in_process_multi_gpu_host_driver(api, sks, oracle, cuda):
         assert_same_bits(H.numpy(), want, "multi-GPU host path, pageable")
     finally:
         sks.c.sks_host_set_device_count(1)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_rect_planar34_layout(api, sks, oracle, cuda, dtype):
+    """sks_cuda_aca_rect_planar_*: the reference's [n,3,4] homogeneous tensors read in
+    place (PY.py:24-37) == the interleaved path, with per-sample and shared corners."""
+    for n in (1, 255, 100_003):
+        _, t = oracle.synth_quads(0, n, 6, 0, dtype)
+        M = np.random.default_rng(n).integers(10, 30, size=(n, 2)).astype(dtype)
+        tar34 = np.ones((n, 3, 4), dtype=dtype)
+        tar34[:, :2, :] = t.reshape(n, 4, 2).transpose(0, 2, 1)
+        src34 = np.ones((n, 3, 4), dtype=dtype)
+        src34[:, 0, :] = M[:, :1] + np.array([0, 128, 0, 128], dtype=dtype)
+        src34[:, 1, :] = M[:, 1:] + np.array([0, 0, 128, 128], dtype=dtype)
+        d_t, d_s = dev(tar34, cuda), dev(src34, cuda)
+        name = "f32" if dtype == np.float32 else "f64"
+        fn = getattr(sks.c, f"sks_cuda_aca_rect_planar_{name}")
+        for normalize in (0, 1):
+            H = torch.full((n * 9 + 16,), 5.0, dtype=TDT[dtype], device=cuda)
+            flag = torch.zeros(n, dtype=torch.uint8, device=cuda)
+            sks.check(fn(d_t.data_ptr(), d_s.data_ptr(), 0.0, 0.0, 128.0, 1.0, H.data_ptr(), n, normalize,
+                         flag.data_ptr(), None), "planar per-sample")
+            want = oracle.aca_rect(t, 0, 0, 128.0, 1.0, M=M, normalize=bool(normalize))
+            assert_same_bits(H[: n * 9].view(n, 9).cpu().numpy(), want, f"planar per-sample n={n}")
+            assert bool((H[n * 9:] == 5.0).all()) and int(flag.sum()) == 0
+            sks.check(fn(d_t.data_ptr(), None, 36.0, 81.0, 50.0, 1.25, H.data_ptr(), n, normalize, None, None),
+                      "planar shared")
+            want = oracle.aca_rect(t, 36.0, 81.0, 50.0, 1.25, normalize=bool(normalize))
+            assert_same_bits(H[: n * 9].view(n, 9).cpu().numpy(), want, f"planar shared n={n}")

@@ -117,3 +117,14 @@ def test_nonfinite_scores_are_never_inliers(api, sks, oracle, cuda, hpt, packed)
             assert np.array_equal(got[:, j], counts[:, j])
     finally:
         sks.c.sks_cuda_set_ransac_tuning(2, 8, 1)
+
+
+def test_more_pairs_than_one_grid_dimension(api, oracle, cuda):
+    """n_pairs > 65535 goes out in blocks of pairs; sampling must not depend on blocking."""
+    P, n_pts, n_hyp = 70_001, 8, 6
+    rng = np.random.default_rng(3)
+    corr = rng.uniform(10, 150, size=(P, n_pts, 4)).astype(np.float32)
+    corr[:, :, 2:] = corr[:, :, :2] * 1.02 + 2.0 + rng.uniform(-0.3, 0.3, size=(P, n_pts, 2)).astype(np.float32)
+    keys = api.ransac_keys(torch.from_numpy(corr).to(cuda), n_hyp, seed=4, thr2=4.0)
+    want = oracle.ransac(corr, n_hyp, seed=4, thr2=4.0)
+    assert np.array_equal(u64(keys), want)
