@@ -139,6 +139,23 @@ int sks_cuda_gather_samples_f64(const double *pool_xyXY, uint32_t pool_size,
                                 const uint32_t *rand4, uint64_t seed, double *src, double *tar,
                                 int64_t n, int layout, int64_t ld, void *stream);
 
+/* Fused gather + solve: the reference's GPU flow get_rand_list -> cal_Homo_ACA /
+ * cal_Homo_SKS (GPU.cu:1449-1464) in ONE kernel -- the sampled quadruples never
+ * touch HBM, only H (AoS or SoA, like the solvers) is written.  Same sampling
+ * rule and arguments as sks_cuda_gather_samples_*. */
+int sks_cuda_gather_aca_f32(const float *pool_xyXY, uint32_t pool_size, const uint32_t *rand4,
+                            uint64_t seed, float *H, int64_t n, int layout, int64_t ld, int flags,
+                            uint8_t *degenerate, void *stream);
+int sks_cuda_gather_aca_f64(const double *pool_xyXY, uint32_t pool_size, const uint32_t *rand4,
+                            uint64_t seed, double *H, int64_t n, int layout, int64_t ld, int flags,
+                            uint8_t *degenerate, void *stream);
+int sks_cuda_gather_sks_f32(const float *pool_xyXY, uint32_t pool_size, const uint32_t *rand4,
+                            uint64_t seed, float *H, int64_t n, int layout, int64_t ld, int flags,
+                            uint8_t *degenerate, void *stream);
+int sks_cuda_gather_sks_f64(const double *pool_xyXY, uint32_t pool_size, const uint32_t *rand4,
+                            uint64_t seed, double *H, int64_t n, int layout, int64_t ld, int flags,
+                            uint8_t *degenerate, void *stream);
+
 /* ---- fused ACA-RANSAC ----------------------------------------------------- */
 /* New (nothing like it in the reference; sampler precedent GPU.cu:52-78).
  * corr: [n_pairs][n_pts][4] = (x,y,X,Y) fp32.  Hypothesis ids

@@ -225,6 +225,24 @@ def gather_samples(pool: torch.Tensor, n: int, seed: int = 11, rand4: torch.Tens
     return src, tar
 
 
+def gather_solve(solver: str, pool: torch.Tensor, n: int, seed: int = 11,
+                 rand4: torch.Tensor | None = None, normalize: bool = True, layout: str = "aos"
+                 ) -> torch.Tensor:
+    """Fused get_rand_list + cal_Homo_* (GPU.cu:1449-1464): n hypotheses straight from
+    a match pool [size,4]; the sampled quadruples never touch HBM."""
+    L = lib()
+    dtype = pool.dtype
+    pool = pool.contiguous()
+    H = torch.empty((n, 9) if layout == "aos" else (9, n), dtype=dtype, device=pool.device)
+    with torch.cuda.device(pool.device):
+        fn = getattr(L.c, f"sks_cuda_gather_{solver}_{_SUFFIX[dtype]}")
+        L.check(fn(_ptr(pool), pool.shape[0], _ptr(rand4), seed, _ptr(H), n,
+                   LAYOUT_AOS if layout == "aos" else LAYOUT_SOA, n,
+                   FLAG_NORMALIZE if normalize else 0, None, _stream_ptr(pool)),
+                "sks_cuda_gather_solve")
+    return H
+
+
 # ------------------------------------------------------------------- RANSAC
 def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
                 samples: torch.Tensor | None = None, hyp_begin: int = 0,

@@ -149,6 +149,27 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
     return launch_ring<SOLVER, T, BIG>(src, tar, M, rp, H, degen, n, normalize, dev, st);
 }
 
+template <int SOLVER, typename T>
+int launch_gather_solve(const T* pool, uint32_t pool_size, const uint32_t* rand4, uint64_t seed, T* H,
+                        int64_t n, int layout, int64_t ld, int flags, uint8_t* degen, void* stream)
+{
+    if (n < 0 || pool_size == 0 || (flags & ~SKS_FLAG_NORMALIZE)) return SKS_ERR_INVALID_ARG;
+    if (layout != SKS_LAYOUT_AOS && layout != SKS_LAYOUT_SOA) return SKS_ERR_INVALID_ARG;
+    if (n > 0 && (pool == nullptr || H == nullptr)) return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n == 0) return SKS_OK;
+    if (!aligned16(pool) || !aligned16(H)) return SKS_ERR_UNALIGNED;
+    if (ld == 0) ld = n;
+    if (ld < n) return SKS_ERR_INVALID_ARG;
+    constexpr int TILE = sizeof(T) == 4 ? 256 : 128;
+    const int64_t grid = (n + TILE - 1) / TILE;
+    k_gather_solve<SOLVER, T, TILE><<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(
+        pool, pool_size, rand4, seed_key(seed), H, degen, n, layout, ld,
+        (flags & SKS_FLAG_NORMALIZE) != 0);
+    return finish_launch();
+}
+
 template <typename T>
 int launch_rect_planar(const T* tar34, const T* src34, RectParams<T> rp, T* H, int64_t n, int flags,
                        uint8_t* degen, void* stream)
@@ -279,6 +300,18 @@ int sks_cuda_gather_samples_f64(const double* pool, uint32_t pool_size, const ui
 {
     return launch_gather<double>(pool, pool_size, rand4, seed, src, tar, n, layout, ld, stream);
 }
+
+#define SKS_DEFINE_GATHER_SOLVE(NAME, SOLVER, T)                                                 \
+    int NAME(const T* pool, uint32_t pool_size, const uint32_t* rand4, uint64_t seed, T* H,     \
+             int64_t n, int layout, int64_t ld, int flags, uint8_t* degenerate, void* stream)   \
+    {                                                                                           \
+        return launch_gather_solve<SOLVER, T>(pool, pool_size, rand4, seed, H, n, layout, ld,    \
+                                              flags, degenerate, stream);                       \
+    }
+SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_aca_f32, SOLVER_ACA, float)
+SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_aca_f64, SOLVER_ACA, double)
+SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_sks_f32, SOLVER_SKS, float)
+SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_sks_f64, SOLVER_SKS, double)
 
 int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
                             const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,

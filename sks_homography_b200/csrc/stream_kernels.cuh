@@ -283,6 +283,67 @@ k_rect_planar34(const T* __restrict__ tar34, const T* __restrict__ src34, RectPa
     store_tile<T, TILE, false>(stage, H, q0, cnt, tid);
 }
 
+// ----------------------------------------------------------- k_gather_solve
+// The reference's GPU flow is get_rand_list -> cal_Homo_* (GPU.cu:1449-1464): the
+// gather writes 16 coordinates per hypothesis to HBM and the solver reads them
+// straight back (256 B of traffic per fp64 hypothesis before any result).  Fused
+// here: each thread draws its four pool indices (r % pool_size, repeats allowed,
+// GPU.cu:55-58; from the caller's [4][n] list or the counter RNG), gathers the
+// matches from the L1/L2-resident pool, solves, and only H leaves the SM.
+template <int SOLVER, typename T, int TILE>
+__global__ void __launch_bounds__(TILE)
+k_gather_solve(const T* __restrict__ pool, uint32_t pool_size, const uint32_t* __restrict__ rand4,
+               uint64_t key, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, int layout,
+               int64_t ld, bool normalize)
+{
+    __shared__ __align__(32) T stage[TILE * 9];
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.x * TILE;
+    const int64_t i = q0 + tid;
+    const int cnt = (int)((n - q0) < (int64_t)TILE ? (n - q0) : (int64_t)TILE);
+    if (tid < cnt) {
+        T s[8], t[8], h[9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t r;
+            if (rand4 != nullptr)
+                r = __ldg(rand4 + (int64_t)k * n + i);
+            else {
+                uint64_t z = key ^ ((uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)k);
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+                r = (uint32_t)((z ^ (z >> 31)) >> 32);
+            }
+            const T* c = pool + 4 * (size_t)(r % pool_size);
+            if constexpr (sizeof(T) == 4) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(c));
+                s[2 * k] = m.x; s[2 * k + 1] = m.y; t[2 * k] = m.z; t[2 * k + 1] = m.w;
+            } else {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(c));
+                const double2 b = __ldg(reinterpret_cast<const double2*>(c) + 1);
+                s[2 * k] = a.x; s[2 * k + 1] = a.y; t[2 * k] = b.x; t[2 * k + 1] = b.y;
+            }
+        }
+        RectParams<T> none{};
+        solve_quad<SOLVER, T>(s, t, T(0), T(0), none, h, normalize);
+        if (layout == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                stage[tid * 9 + k] = h[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                H[k * ld + i] = h[k];
+        }
+        if (degen != nullptr)
+            degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
+    }
+    if (layout == 0) {
+        __syncthreads();
+        store_tile<T, TILE, false>(stage, H, q0, cnt, tid);
+    }
+}
+
 // -------------------------------------------------------------- k_aos_ring
 template <int SOLVER, typename T, int TILE>
 struct RingLayout {

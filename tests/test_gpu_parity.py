@@ -303,3 +303,22 @@ def test_rect_planar34_layout(api, sks, oracle, cuda, dtype):
                       "planar shared")
             want = oracle.aca_rect(t, 36.0, 81.0, 50.0, 1.25, normalize=bool(normalize))
             assert_same_bits(H[: n * 9].view(n, 9).cpu().numpy(), want, f"planar shared n={n}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("solver", ["aca", "sks"])
+def test_fused_gather_solve_equals_gather_then_solve(api, oracle, cuda, solver, dtype):
+    """One kernel for the reference's get_rand_list -> cal_Homo_* flow (GPU.cu:1449-1464)."""
+    rng = np.random.default_rng(5)
+    pool = rng.uniform(7, 790, size=(2540, 4)).astype(dtype)
+    n = 100_003
+    rand4 = rng.integers(0, 2**32, size=(4, n), dtype=np.uint32)
+    d_pool, d_rand = dev(pool, cuda), dev(rand4, cuda)
+    for r4 in (d_rand, None):
+        src, tar = api.gather_samples(d_pool, n, seed=9, rand4=r4)
+        want = oracle.solve(solver, src.cpu().numpy(), tar.cpu().numpy())
+        H = api.gather_solve(solver, d_pool, n, seed=9, rand4=r4)
+        assert_same_bits(H.cpu().numpy(), want, "fused aos")
+        Hs = api.gather_solve(solver, d_pool, n, seed=9, rand4=r4, normalize=False, layout="soa")
+        assert_same_bits(Hs.cpu().numpy().T, oracle.solve(solver, src.cpu().numpy(), tar.cpu().numpy(),
+                                                            normalize=False), "fused soa")

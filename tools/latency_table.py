@@ -59,3 +59,19 @@ for n in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
         t_our = time_us(ours)
         t_g = graph_us(ours)
         print(f"{n:9d} | {solver:6s} | {t_ref:12.2f} | {t_our:9.2f} | {t_g:19.2f}", flush=True)
+
+
+# The reference's whole GPU flow for one batch: get_rand_list + cal_Homo (GPU.cu:1449-1464)
+# vs the fused gather+solve kernel, N = 2^24 hypotheses from a 2540-match pool, fp64 SoA.
+import numpy as np
+n = 1 << 24
+pool = torch.from_numpy(np.random.default_rng(0).uniform(7, 790, size=(2540, 4))).to(dev)
+rand4 = torch.randint(0, 2**31, (4, n), dtype=torch.int64, device=dev).to(torch.int32)
+H = torch.empty((9, n), dtype=torch.float64, device=dev)
+for solver in ("aca", "sks"):
+    def two_kernels():
+        s, t = api.gather_samples(pool, n, rand4=rand4, layout="soa")
+        api.solve(solver, s, t, result=H, normalize=False, layout="soa")
+    t2 = time_us(two_kernels, 20)
+    t1 = time_us(lambda: api.gather_solve(solver, pool, n, rand4=rand4, normalize=False, layout="soa"), 20)
+    print(f"N=2^24 {solver}: gather kernel + solver kernel {t2:9.1f} us | fused gather+solve {t1:9.1f} us  ({t2 / t1:.2f}x)")
