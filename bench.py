@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--rounds", type=int, default=8, help="RANSAC rounds per CTA")
     ap.add_argument("--packed", type=int, default=-1, help="RANSAC FFMA2 scoring (0|1)")
     ap.add_argument("--log2n", type=int, default=None, help="quadruples per GPU = 2^log2n")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: 2^log2n quadruples in TOTAL, sharded contiguously over the ranks "
+                         "(BASELINE configs[2]: --workload rect_f32 --log2n 28 --strong)")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
@@ -225,10 +228,13 @@ def main():
 
     solver, dt, bytes_per_h, log2n, dist_id = WORKLOADS[args.workload]
     log2n = args.log2n if args.log2n is not None else log2n
-    n = 1 << log2n
+    if args.strong:
+        begin, n = L.shard_range(1 << log2n, rank, world)     # contiguous shard of a fixed total
+    else:
+        n = 1 << log2n
+        begin = rank * n                              # this rank's shard of the global index space
     tdt = torch.float32 if dt == "f32" else torch.float64
     normalize = not args.no_normalize
-    begin = rank * n                                  # this rank's shard of the global index space
 
     # ---- inputs resident in HBM, generated on the device -----------------------
     src, tar = api.synth_quads(n, seed=args.seed, dist=dist_id, dtype=tdt, device=dev, begin=begin,
@@ -267,7 +273,8 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
     ms_per_step = total_ms_max / args.steps
-    value = world * n / (ms_per_step * 1e-3)
+    n_total = (1 << log2n) if args.strong else world * n
+    value = n_total / (ms_per_step * 1e-3)
 
     peak, peak_src = peaks()
     mean_launch_ms = statistics.mean(per_launch_ms)
@@ -360,9 +367,10 @@ def main():
         line = {
             "impl": "ours", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dt,
-            "data": "synthetic",
-            "config": {"workload": f"batched {solver.upper()} {dt} 2^{log2n} quadruples per GPU, "
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": dt, "data": "synthetic",
+            "config": {"workload": f"batched {solver.upper()} {dt} 2^{log2n} quadruples "
+                                   f"{'in total, sharded over the ranks' if args.strong else 'per GPU'}, "
                                    f"{args.layout.upper()} in/out, "
                                    f"{'h33-normalised' if normalize else 'up to scale'}",
                        "quadruples_per_gpu": n, "layout": args.layout, "variant": args.variant,
