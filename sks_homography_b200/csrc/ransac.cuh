@@ -39,6 +39,9 @@
 #ifndef SKS_RANSAC_HYP_MAJOR
 #define SKS_RANSAC_HYP_MAJOR 1
 #endif
+#ifndef SKS_RANSAC_SCALAR_RESID
+#define SKS_RANSAC_SCALAR_RESID 0
+#endif
 #ifndef SKS_RANSAC_STAGED
 #define SKS_RANSAC_STAGED 0      // 1 = stage-major volatile-asm scorer (kept for the record: ptxas
                                  // re-interleaves it, measured 70 % vs 74.6 % for the plain form)
@@ -104,8 +107,15 @@ __device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&h)[9], const f
     const float2 u = __ffma2_rn(h[0], x, __ffma2_rn(h[1], y, h[2]));
     const float2 v = __ffma2_rn(h[3], x, __ffma2_rn(h[4], y, h[5]));
     const float2 w = __ffma2_rn(h[6], x, __ffma2_rn(h[7], y, h[8]));
+#if SKS_RANSAC_SCALAR_RESID
+    // residuals as four scalar FFMAs: a 3-pair FFMA2 needs six register reads (three
+    // cycles), whereas scalar FFMAs with -X / -Y served by the reuse cache run at full rate
+    const float2 du = make_float2(__fmaf_rn(nX.x, w.x, u.x), __fmaf_rn(nX.y, w.y, u.y));
+    const float2 dv = make_float2(__fmaf_rn(nY.x, w.x, v.x), __fmaf_rn(nY.y, w.y, v.y));
+#else
     const float2 du = __ffma2_rn(nX, w, u);
     const float2 dv = __ffma2_rn(nY, w, v);
+#endif
     const float2 e = __ffma2_rn(dv, dv, __fmul2_rn(du, du));
     const float2 acc = __ffma2_rn(nthr2, __fmul2_rn(w, w), e);
     return (__float_as_uint(acc.x) >> 31) + (__float_as_uint(acc.y) >> 31);

@@ -322,3 +322,26 @@ def test_fused_gather_solve_equals_gather_then_solve(api, oracle, cuda, solver, 
         Hs = api.gather_solve(solver, d_pool, n, seed=9, rand4=r4, normalize=False, layout="soa")
         assert_same_bits(Hs.cpu().numpy().T, oracle.solve(solver, src.cpu().numpy(), tar.cpu().numpy(),
                                                             normalize=False), "fused soa")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("solver", ["aca", "sks"])
+def test_extreme_magnitudes_overflow_and_denormals(api, oracle, cuda, solver, dtype):
+    """Un-normalised entries are degree 7-9 polynomials of the coordinates (README.md:54):
+    huge inputs overflow to inf/NaN, tiny ones run through denormals.  IEEE arithmetic
+    without flush-to-zero must reproduce the reference bit for bit in both regimes."""
+    n = 20_000
+    s, t = oracle.synth_quads(0, n, 3, 1, dtype)
+    scales = [1e-12, 1e-7, 1e-4, 1e4, 1e7, 1e12] if dtype == np.float32 else [1e-60, 1e-35, 1e30, 1e45]
+    for sc in scales:
+        ss, tt = (s * dtype(sc)).astype(dtype), (t * dtype(sc)).astype(dtype)
+        for normalize in (True, False):
+            want = oracle.solve(solver, ss, tt, normalize=normalize)
+            flag = torch.zeros(n, dtype=torch.uint8, device=cuda)
+            H = api.solve(solver, dev(ss, cuda), dev(tt, cuda), normalize=normalize, degenerate=flag)
+            assert_same_bits(H.cpu().numpy(), want, f"{solver} scale {sc} normalize={normalize}")
+            assert np.array_equal(flag.cpu().numpy(), oracle.degenerate(want, normalize))
+    # mixed: only the target plane is tiny (denormal products against normal ones)
+    tt = (t * dtype(1e-30 if dtype == np.float32 else 1e-250)).astype(dtype)
+    assert_same_bits(api.solve(solver, dev(s, cuda), dev(tt, cuda)).cpu().numpy(), oracle.solve(solver, s, tt),
+                     "tiny target plane")

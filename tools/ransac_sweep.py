@@ -10,9 +10,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "tools", "_variants")
-VARIANTS = {f"rs_u{u}_hm{hm}": [f"-DSKS_RANSAC_UNROLL={u}", f"-DSKS_RANSAC_HYP_MAJOR={hm}", "-DSKS_RANSAC_STAGED=0"]
-            for u in (2, 8) for hm in (0, 1)}
-VARIANTS.update({f"rs_staged_u{u}": [f"-DSKS_RANSAC_UNROLL={u}", "-DSKS_RANSAC_STAGED=1"] for u in (1, 2, 4)})
+VARIANTS = {}
+for u in (2, 4, 8):
+    for hm in (0, 1):
+        for sr in (0, 1):
+            VARIANTS[f"rs_u{u}_hm{hm}_sr{sr}"] = [f"-DSKS_RANSAC_UNROLL={u}", f"-DSKS_RANSAC_HYP_MAJOR={hm}",
+                                                 f"-DSKS_RANSAC_SCALAR_RESID={sr}", "-DSKS_RANSAC_STAGED=0"]
 
 if "--build" in sys.argv:
     from sks_homography_b200 import build as b
