@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--hpt", type=int, default=0, help="RANSAC hypotheses per thread (2|4)")
     ap.add_argument("--rounds", type=int, default=8, help="RANSAC rounds per CTA")
     ap.add_argument("--packed", type=int, default=-1, help="RANSAC FFMA2 scoring (0|1)")
+    ap.add_argument("--peer-reduce", action="store_true",
+                    help="RANSAC: merge the winners with the hand-written NVLink peer max-reduce "
+                         "instead of the NCCL all-reduce")
     ap.add_argument("--log2n", type=int, default=None, help="quadruples per GPU = 2^log2n")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: 2^log2n quadruples in TOTAL, sharded contiguously over the ranks "
@@ -445,11 +448,15 @@ def run_ransac(args, api, L, dev, rank, world, local):
     hb, hc = sd.shard_range(n_hyp, rank, world)
     keys = torch.zeros(P, dtype=torch.int64, device=dev)
     res = {}
+    reducer = sd.PeerReducer(P, dev) if args.peer_reduce else None
 
     def step():
         keys.zero_()
         api.ransac_keys(corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys)
-        sd.merge_keys(keys)
+        if reducer is not None:
+            reducer.max_reduce_(keys)
+        else:
+            sd.merge_keys(keys)
         res["H"], res["cnt"], _ = api.ransac_finalize(corr, n_hyp, args.seed, thr2, keys)
 
     def barrier():
@@ -518,14 +525,19 @@ def run_ransac(args, api, L, dev, rank, world, local):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"fused ACA-RANSAC {P} pairs x {n_pts} matches x {n_hyp} hypotheses, "
-                                   f"hypotheses sharded over {world} GPU(s), one int64 max all-reduce",
+                                   f"hypotheses sharded over {world} GPU(s), "
+                                   + ("winners merged by NVLink peer atomics (csrc/peer.cuh)" if reducer
+                                      else "one int64 max all-reduce (NCCL)"),
                        "thr2": thr2, "seed": args.seed,
                        "l2": "compute-bound; matches (64 KiB/pair) live in shared memory"},
             "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
             "clocks": clocks, "parity": parity,
             "mean_inlier_fraction_of_winner": float(cnt.mean().item()) / n_pts,
+            "peer_reduce_timed_out": reducer.timed_out() if reducer else None,
         }
         print(json.dumps(line))
+    if reducer is not None:
+        reducer.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

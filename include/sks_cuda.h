@@ -192,6 +192,28 @@ int sks_cuda_synth_quads_f64(double *src, double *tar, int64_t begin, int64_t co
 int sks_cuda_synth_corr_f32(float *corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
                             uint64_t seed, int inlier_permille, float noise, void *stream);
 
+/* ---- NVLink peer exchange: hand-written max-reduce of the RANSAC keys ------- */
+/* Optional replacement for the one NCCL all-reduce of the multi-GPU RANSAC step
+ * (one process per GPU, same node).  Each rank allocates an exchange block for
+ * n_keys packed keys, exports its 64-byte CUDA-IPC handle, and opens every
+ * peer's.  A reduce is then sks_cuda_peer_push_max (system-scope atomicMax of
+ * the local keys into every rank's block over NVLink + arrival signal) followed
+ * by sks_cuda_peer_wait (bounded device-side wait for all `world` arrivals, then
+ * the reduced keys are copied to keys_out; *status_dev = 1 on timeout).  `epoch`
+ * counts reduces since allocation (0, 1, 2, ...) and must advance in lock-step
+ * on all ranks; peer_blocks[g] is rank g's block as mapped in THIS process
+ * (peer_blocks[rank] = the own block). */
+int sks_cuda_peer_alloc(void **block, int64_t n_keys);
+int sks_cuda_peer_free(void *block);
+int sks_cuda_peer_export(void *block, void *handle64);
+int sks_cuda_peer_open(const void *handle64, void **block);
+int sks_cuda_peer_close(void *block);
+int sks_cuda_peer_push_max(const unsigned long long *local_keys, int64_t n_keys,
+                           void *const *peer_blocks, int world, int rank, uint64_t epoch,
+                           void *stream);
+int sks_cuda_peer_wait(void *own_block, int world, uint64_t epoch, unsigned long long *keys_out,
+                       int64_t n_keys, int *status_dev, double timeout_s, void *stream);
+
 /* ---- multi-GPU helpers ----------------------------------------------------- */
 /* Contiguous shard [begin, begin+count) of n units for `rank` of `world`
  * (SURVEY.md 8(e)); the streaming solvers need no collective at all. */

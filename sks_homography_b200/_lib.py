@@ -70,6 +70,13 @@ _SIGS = {
     "sks_cuda_synth_quads_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _int, _int, _i64, _vp]),
     "sks_cuda_synth_quads_f64": (_int, [_vp, _vp, _i64, _i64, _u64, _int, _int, _i64, _vp]),
     "sks_cuda_synth_corr_f32": (_int, [_vp, _i64, _i64, _i32, _u64, _int, _f32, _vp]),
+    "sks_cuda_peer_alloc": (_int, [C.POINTER(_vp), _i64]),
+    "sks_cuda_peer_free": (_int, [_vp]),
+    "sks_cuda_peer_export": (_int, [_vp, _vp]),
+    "sks_cuda_peer_open": (_int, [_vp, C.POINTER(_vp)]),
+    "sks_cuda_peer_close": (_int, [_vp]),
+    "sks_cuda_peer_push_max": (_int, [_vp, _i64, C.POINTER(_vp), _int, _int, _u64, _vp]),
+    "sks_cuda_peer_wait": (_int, [_vp, _int, _u64, _vp, _i64, _vp, C.c_double, _vp]),
     "sks_cuda_shard_range": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "sks_cuda_launch_count": (_i64, []),
     "sks_cuda_reset_launch_count": (None, []),

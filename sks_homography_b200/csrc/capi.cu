@@ -4,11 +4,13 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 #include <cuda_runtime.h>
 
 #include "../../include/sks_cuda.h"
+#include "peer.cuh"
 #include "ransac.cuh"
 #include "stream_kernels.cuh"
 #include "synth.cuh"
@@ -406,6 +408,72 @@ int sks_cuda_synth_corr_f32(float* corr, int64_t pair_begin, int64_t n_pairs, in
     k_synth_corr<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(corr), pair_begin, n_pairs, n_pts, seed_key(seed),
         inlier_permille, noise);
+    return finish_launch();
+}
+
+// ---- NVLink peer exchange (hand-written max-reduce of the RANSAC keys) ----------
+int sks_cuda_peer_alloc(void** block, int64_t n_keys)
+{
+    if (block == nullptr || n_keys <= 0) return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    const size_t bytes = sizeof(PeerBlock) + 2 * (size_t)n_keys * sizeof(unsigned long long);
+    cudaError_t e = cudaMalloc(block, bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*block, 0, bytes);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned long long nk = (unsigned long long)n_keys;
+    e = cudaMemcpy(&static_cast<PeerBlock*>(*block)->n_keys, &nk, sizeof nk, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaDeviceSynchronize();
+}
+int sks_cuda_peer_free(void* block) { return (int)cudaFree(block); }
+int sks_cuda_peer_export(void* block, void* handle64)
+{
+    if (block == nullptr || handle64 == nullptr) return SKS_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    return (int)cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), block);
+}
+int sks_cuda_peer_open(const void* handle64, void** block)
+{
+    if (block == nullptr || handle64 == nullptr) return SKS_ERR_INVALID_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    return (int)cudaIpcOpenMemHandle(block, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int sks_cuda_peer_close(void* block) { return (int)cudaIpcCloseMemHandle(block); }
+
+int sks_cuda_peer_push_max(const unsigned long long* local_keys, int64_t n_keys,
+                           void* const* peer_blocks, int world, int rank, uint64_t epoch,
+                           void* stream)
+{
+    if (local_keys == nullptr || peer_blocks == nullptr || n_keys <= 0 || world < 1 ||
+        world > kMaxPeers || rank < 0 || rank >= world)
+        return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    PeerTable tab{};
+    for (int g = 0; g < world; ++g) {
+        if (peer_blocks[g] == nullptr) return SKS_ERR_INVALID_ARG;
+        tab.blk[g] = static_cast<PeerBlock*>(peer_blocks[g]);
+    }
+    const unsigned grid = (unsigned)((n_keys + 255) / 256);
+    k_peer_push_max<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(local_keys, n_keys, tab, world,
+                                                                         rank, epoch);
+    return finish_launch();
+}
+
+int sks_cuda_peer_wait(void* own_block, int world, uint64_t epoch, unsigned long long* keys_out,
+                       int64_t n_keys, int* status_dev, double timeout_s, void* stream)
+{
+    if (own_block == nullptr || keys_out == nullptr || n_keys <= 0 || world < 1)
+        return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (timeout_s <= 0) timeout_s = 5.0;
+    const long long cycles = (long long)(timeout_s * 1.9e9);
+    k_peer_wait_copy<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<PeerBlock*>(own_block), world, epoch, keys_out, n_keys, status_dev, cycles);
     return finish_launch();
 }
 

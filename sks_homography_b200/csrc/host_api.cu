@@ -79,8 +79,9 @@ void free_ctx(HostCtx* c)
     delete c;
 }
 
-int get_ctx(int dev, int64_t need_in, int64_t need_out, bool stage_in, bool stage_out,
-            HostCtx** out)
+// Find or create the per-device context (table lock only; no device memory is
+// touched here so a batch running on the device is not disturbed).
+int get_ctx(int dev, HostCtx** out)
 {
     std::lock_guard<std::mutex> table(g_mu);
     HostCtx* c = nullptr;
@@ -95,6 +96,14 @@ int get_ctx(int dev, int64_t need_in, int64_t need_out, bool stage_in, bool stag
             CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         }
     }
+    *out = c;
+    return SKS_OK;
+}
+
+// Grow the ring's device / pinned buffers.  Caller holds c->mu, so no batch is in
+// flight on these buffers.
+int ensure_capacity(HostCtx* c, int64_t need_in, int64_t need_out, bool stage_in, bool stage_out)
+{
     if (need_in > c->cap_in) {
         for (Slot& s : c->slot)
             for (int k = 0; k < 3; ++k) {
@@ -129,7 +138,6 @@ int get_ctx(int dev, int64_t need_in, int64_t need_out, bool stage_in, bool stag
             CK(cudaHostAlloc(&s.p_out, (size_t)c->cap_out, cudaHostAllocDefault));
         c->staged_out = true;
     }
-    *out = c;
     return SKS_OK;
 }
 
@@ -176,10 +184,11 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
     for (int k = 0; k < n_in; ++k) stage_in = stage_in || !is_pinned(in[k]);
     const bool stage_out = !is_pinned(out);
     HostCtx* c = nullptr;
-    if (int rc = get_ctx(dev, chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T), stage_in,
-                         stage_out, &c))
-        return rc;
+    if (int rc = get_ctx(dev, &c)) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
+    if (int rc = ensure_capacity(c, chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T),
+                                 stage_in, stage_out))
+        return rc;
 
     auto drain = [&](Slot& s) -> int {   // finish the chunk this slot last produced
         if (s.pending_off < 0) return SKS_OK;

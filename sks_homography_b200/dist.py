@@ -40,14 +40,89 @@ def merge_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     return keys
 
 
+class PeerReducer:
+    """Hand-written NVLink replacement for the one NCCL all-reduce of the RANSAC step
+    (csrc/peer.cuh): every rank's keys are max-combined into every rank's exchange
+    block with system-scope atomics over peer memory; two small kernels per rank, no
+    collective call inside the step.  Setup (once) exchanges CUDA-IPC handles through
+    torch.distributed.  Works for world == 1 too (the block is then only the own one)."""
+
+    def __init__(self, n_keys: int, device, group=None, timeout_s: float = 5.0):
+        import ctypes as C
+        self.L = lib()
+        self.group = group
+        self.rank, self.world = world(group)
+        self.n_keys = int(n_keys)
+        self.device = torch.device(device)
+        self.timeout_s = float(timeout_s)
+        self.epoch = 0
+        self._opened = []
+        with torch.cuda.device(self.device):
+            own = C.c_void_p()
+            self.L.check(self.L.c.sks_cuda_peer_alloc(C.byref(own), self.n_keys), "sks_cuda_peer_alloc")
+            self.own = own
+            handle = (C.c_ubyte * 64)()
+            self.L.check(self.L.c.sks_cuda_peer_export(own, handle), "sks_cuda_peer_export")
+            handles = [bytes(handle)]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self.blocks = (C.c_void_p * self.world)()
+            for g in range(self.world):
+                if g == self.rank:
+                    self.blocks[g] = own
+                else:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[g])
+                    self.L.check(self.L.c.sks_cuda_peer_open(buf, C.byref(p)), "sks_cuda_peer_open")
+                    self.blocks[g] = p
+                    self._opened.append(p)
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            if self.world > 1:
+                dist.barrier(group=group)      # every block exists and is zeroed before the first push
+
+    def max_reduce_(self, keys: torch.Tensor) -> torch.Tensor:
+        """In-place global max of the packed keys (int64 view) across the ranks."""
+        if keys.numel() != self.n_keys or keys.dtype != torch.int64 or not keys.is_contiguous():
+            raise ValueError("keys must be a contiguous int64 tensor of n_keys elements")
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            self.L.check(self.L.c.sks_cuda_peer_push_max(keys.data_ptr(), self.n_keys, self.blocks, self.world,
+                                                         self.rank, self.epoch, st), "sks_cuda_peer_push_max")
+            self.L.check(self.L.c.sks_cuda_peer_wait(self.own, self.world, self.epoch, keys.data_ptr(),
+                                                     self.n_keys, self.status.data_ptr(), self.timeout_s, st),
+                         "sks_cuda_peer_wait")
+        self.epoch += 1
+        return keys
+
+    def timed_out(self) -> bool:
+        return bool(self.status.item())
+
+    def close(self) -> None:
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            for p in self._opened:
+                self.L.c.sks_cuda_peer_close(p)
+            self._opened = []
+            if self.own is not None:
+                self.L.c.sks_cuda_peer_free(self.own)
+                self.own = None
+
+
 def ransac_aca(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
-               samples: torch.Tensor | None = None, group=None, want_mask: bool = False):
+               samples: torch.Tensor | None = None, group=None, want_mask: bool = False,
+               reducer: "PeerReducer | None" = None):
     """Hypothesis-sharded fused ACA-RANSAC.  Every rank holds all pairs' matches
     `corr` [P, n_pts, 4]; returns (H_best [P,9], inlier_count [P], hyp_id [P], mask)."""
     from . import api
     begin, count = shard_range(n_hyp, group=group)
     keys = api.ransac_keys(corr, n_hyp, seed, thr2, samples, begin, count)
-    merge_keys(keys, group)
+    if reducer is not None:
+        reducer.max_reduce_(keys)      # NVLink peer atomics instead of the NCCL all-reduce
+    else:
+        merge_keys(keys, group)
     H, cnt, mask = api.ransac_finalize(corr, n_hyp, seed, thr2, keys, samples, want_mask)
     _, hyp = api.decode_keys(keys)
     return H, cnt, hyp, mask

@@ -128,3 +128,19 @@ def test_more_pairs_than_one_grid_dimension(api, oracle, cuda):
     keys = api.ransac_keys(torch.from_numpy(corr).to(cuda), n_hyp, seed=4, thr2=4.0)
     want = oracle.ransac(corr, n_hyp, seed=4, thr2=4.0)
     assert np.array_equal(u64(keys), want)
+
+
+def test_peer_reducer_single_rank_epochs(api, cuda):
+    """csrc/peer.cuh on one GPU (world = 1): buffers alternate by epoch parity and the
+    arrival counter is monotonic, so repeated reduces need no reset."""
+    from sks_homography_b200 import dist as sd
+    red = sd.PeerReducer(1000, cuda)
+    try:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        for epoch in range(7):
+            keys = torch.randint(0, 2**62, (1000,), generator=g, dtype=torch.int64).to(cuda)
+            want = keys.clone()
+            red.max_reduce_(keys)
+            assert torch.equal(keys, want) and not red.timed_out()
+    finally:
+        red.close()
