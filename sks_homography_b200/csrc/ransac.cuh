@@ -19,12 +19,15 @@
 //
 // Mapping: a CTA owns one image pair and a contiguous chunk of hypothesis ids.
 // The pair's correspondences (x,y,X,Y) are pulled into shared memory once by
-// the bulk-copy engine (64 KiB for 4096 points); every thread then carries HPT
-// hypotheses in registers and walks the tile with warp-uniform (broadcast)
-// 16-byte shared loads, so the inner loop is pure FP32 pipe work.  The best
-// (count, lowest id) is reduced with warp shuffles, then one 64-bit atomicMax
-// per CTA.  Bound: FP32 pipe (~12 FP32 + 2 integer instructions per
-// hypothesis x point), not HBM.
+// the bulk-copy engine (64 KiB for 4096 points) and re-laid out in place as
+// pairs; every thread then carries HPT hypotheses in registers and walks the
+// tile with warp-uniform (broadcast) 16-byte shared loads, scoring two matches
+// per instruction with sm_100a's packed FFMA2 / FMUL2, so the inner loop is pure
+// FP32 pipe work: 12 packed FP32 + 2 LEA.HI per two hypothesis x match
+// evaluations.  The best (count, lowest id) is reduced with warp shuffles, then
+// one 64-bit atomicMax per CTA.  Bound: FP32 pipe, more precisely its register
+// operand bandwidth (tools/ubench/fma_peak.cu: an FFMA2 reading three fresh
+// register pairs issues at 2/3 rate), not HBM.
 #pragma once
 #include <cstdint>
 
