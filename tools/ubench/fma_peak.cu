@@ -11,6 +11,8 @@ constexpr int ITERS = 4096;
 // MODE 2: FFMA2, 8 chains of pairs, distinct pair operands
 // MODE 3: FFMA2, broadcast scalar a (the .F32 form), shared pair b
 // MODE 4: FFMA2, acc = fma(acc, acc, c)   (squares: one source register pair)
+// MODE 5/6: FFMA2 and scalar FFMA interleaved (do the heavy and lite FMA pipes add up?)
+//           (MODE 6 reports FMA/clk as if 2 per op; true count is 2.5 -> multiply by 1.25)
 template <int MODE>
 __global__ void __launch_bounds__(256) k(float* out, float seed)
 {
@@ -33,6 +35,8 @@ __global__ void __launch_bounds__(256) k(float* out, float seed)
             if (MODE == 2) C[i] = __ffma2_rn(A[i], B[i], C[i]);
             if (MODE == 3) C[i] = __ffma2_rn(make_float2(a[i], a[i]), B[0], C[i]);
             if (MODE == 4) C[i] = __ffma2_rn(C[i], B[0], A[i]);
+            if (MODE == 5) { C[i] = __ffma2_rn(make_float2(a[i], a[i]), B[0], C[i]); c[i] = __fmaf_rn(a[i], b[0], c[i]); }
+            if (MODE == 6) { C[i] = __ffma2_rn(make_float2(a[i], a[i]), B[0], C[i]); if (i < 4) c[i] = __fmaf_rn(a[i], b[0], c[i]); }
         }
     }
     float s = 0;
@@ -68,5 +72,7 @@ int main()
     run<2>("FFMA2 3 distinct register pairs", 2);
     run<3>("FFMA2 broadcast scalar x shared pair", 2);
     run<4>("FFMA2 acc as multiplicand", 2);
+    run<5>("mix: 8 FFMA2 + 8 FFMA per iteration (reuse forms)", 3);
+    run<6>("mix: 8 FFMA2 + 4 FFMA per iteration (reuse forms)", 2);
     return 0;
 }
