@@ -493,7 +493,10 @@ def run_ransac(args, api, L, dev, rank, world, local):
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": f"148 SM x 128 lanes x 2 x {mhz:.0f} MHz (SM clock sampled under load) x {world} GPU",
-                "flop_per_hypothesis_point": 22, "flop_per_hypothesis": 97}
+                "flop_per_hypothesis_point": 22, "flop_per_hypothesis": 97,
+                # tools/ubench/fma_peak.cu on this pool's B200s: 121.8 of the nominal 128 FMA/clk/SM
+                # are attainable with reuse-friendly operands, 84.7 with three fresh register pairs
+                "frac_of_measured_fma_peak": achieved / (peak * 121.8 / 128.0)}
 
     # parity at full size: a few pairs against the CPU oracle on a hypothesis prefix,
     # and (multi-GPU) merged keys == single-GPU keys on the same pairs
