@@ -1,0 +1,51 @@
+"""bench.py output contract: one JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+             "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+
+
+def run_bench(*args, env=None):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True,
+                         text=True, env={**os.environ, **(env or {})}, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, res.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line(reflib):
+    """`--impl reference`: the reference's own C++ on the host cores, same line shape."""
+    d = run_bench("--impl", "reference", "--steps", "2", "--warmup", "3", "--ref-log2n", "16")
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["unit"] == "homographies/s" and d["value"] > 1e5 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and "workload" in d["config"]
+
+
+def test_reference_arm_non_zero_ranks_exit_quietly():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"},
+                         timeout=120)
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_ours_arm_line(cuda):
+    d = run_bench("--steps", "3", "--warmup", "3", "--log2n", "20", "--cpu-log2n", "18", "--no-gpu-baseline")
+    assert d["impl"] == "ours" and BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    assert d["n_gpus"] == 1 and d["dtype"] == "f32" and d["scaling"] == "weak" and d["gpu_launches"] == 3
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == (1 << 20) * 64 and e["d2h_bytes_per_step"] == (1 << 20) * 36
+    assert e["parity_vs_device_path"] == "bit-exact" and 0 < e["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["parity_gpu_vs_cpu"]["mismatching_elements"] == 0
