@@ -485,15 +485,16 @@ def run_ransac(args, api, L, dev, rank, world, local):
     ms_per_step = float(tmax.item()) / args.steps
     value = P * n_hyp / (ms_per_step * 1e-3)
 
-    # FP32 roofline: 22 flop per hypothesis x point + 97 per hypothesis
-    flops = P * float(n_hyp) * (97.0 + 22.0 * n_pts)
+    # FP32 roofline: 21 flop per hypothesis x point (8 FMA + 1 MUL + 2 FMA once the threshold is
+    # folded into the operands; SURVEY.md 8(d) counted 22 for the unfolded form) + 97 + 6 per hypothesis
+    flops = P * float(n_hyp) * (103.0 + 21.0 * n_pts)
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
     peak = 148 * 128 * 2 * mhz * 1e6 / 1e12 * world
     achieved = flops / (ms_per_step * 1e-3) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": f"148 SM x 128 lanes x 2 x {mhz:.0f} MHz (SM clock sampled under load) x {world} GPU",
-                "flop_per_hypothesis_point": 22, "flop_per_hypothesis": 97,
+                "flop_per_hypothesis_point": 21, "flop_per_hypothesis": 103,
                 # tools/ubench/fma_peak.cu on this pool's B200s: 121.8 of the nominal 128 FMA/clk/SM
                 # are attainable with reuse-friendly operands, 84.7 with three fresh register pairs
                 "frac_of_measured_fma_peak": achieved / (peak * 121.8 / 128.0)}
@@ -520,6 +521,59 @@ def run_ransac(args, api, L, dev, rank, world, local):
         parity = {"pairs_checked": 3, "hypotheses_checked": nh,
                   "keys_equal_cpu_oracle": bool(np.array_equal(got, want)),
                   "sharded_equals_unsharded": full1}
+    # e2e: the same step with the matches in pinned HOST memory -- H2D of every pair's matches,
+    # scoring, winner merge, finalize, D2H of the models and inlier counts inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_corr = corr.cpu().pin_memory()
+        d_corr = torch.empty_like(corr)
+        h_H = torch.empty((P, 9), dtype=torch.float32).pin_memory()
+        h_cnt = torch.empty(P, dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            d_corr.copy_(h_corr, non_blocking=True)
+            keys.zero_()
+            api.ransac_keys(d_corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys)
+            if reducer is not None:
+                reducer.max_reduce_(keys)
+            else:
+                sd.merge_keys(keys)
+            H, c, _ = api.ransac_finalize(d_corr, n_hyp, args.seed, thr2, keys)
+            h_H.copy_(H, non_blocking=True)
+            h_cnt.copy_(c, non_blocking=True)
+
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / args.e2e_steps
+        e2e = {"value": P * n_hyp / (e2e_ms * 1e-3), "unit": "hypotheses/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": corr.numel() * 4, "d2h_bytes_per_step": P * 9 * 4 + P * 4,
+               "models_equal_device_path": bool(torch.equal(h_H, res["H"].cpu()))}
+
+    # CPU baseline: the oracle's scalar port of the same definition on one host core, on a bounded
+    # sample (one pair, a prefix of its hypothesis ids)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        import time
+        from oracle.oracle import Oracle
+        o = Oracle()
+        sub = corr[:1].cpu().numpy()
+        nh = min(n_hyp, max(1024, int(1e9 // max(n_pts, 1))))
+        t0 = time.perf_counter()
+        o.ransac(sub, nh, args.seed, thr2)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nh / dt, "unit": "hypotheses/s", "cores": 1, "kind": "port",
+               "sample": f"1 pair x {n_pts} matches x {nh} hypotheses, oracle/sks_oracle.c "
+                         f"(gcc -O2 -ffp-contract=off), {dt:.1f} s"}
+
     if rank == 0:
         cnt = res["cnt"].float()
         line = {
@@ -533,7 +587,7 @@ def run_ransac(args, api, L, dev, rank, world, local):
                                       else "one int64 max all-reduce (NCCL)"),
                        "thr2": thr2, "seed": args.seed,
                        "l2": "compute-bound; matches (64 KiB/pair) live in shared memory"},
-            "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "parity": parity,
             "mean_inlier_fraction_of_winner": float(cnt.mean().item()) / n_pts,
             "peer_reduce_timed_out": reducer.timed_out() if reducer else None,

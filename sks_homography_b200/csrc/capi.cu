@@ -26,7 +26,7 @@ std::atomic<int> g_stages{4};
 std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
 std::atomic<int> g_wide{1};           // direct kernel: 256-bit loads/stores when 32-byte aligned
 std::atomic<int> g_ransac_hpt{2};     // hypotheses per thread in the RANSAC kernel (2 or 4)
-std::atomic<int> g_ransac_packed{1};  // 1 = FFMA2/FMUL2 two-matches-per-instruction scoring (measured best)
+std::atomic<int> g_ransac_packed{1};  // scorer: 0 scalar FFMA, 1 FFMA2 over two matches, 2 FFMA2 over two hypotheses
 std::atomic<int> g_ransac_threads{256};
 std::atomic<int> g_ransac_rounds{8};  // rounds per CTA (chunk = rounds * 256 * hpt hypotheses)
 
@@ -331,20 +331,17 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
     const int32_t tile_pts = n_pts < kRansacMaxTilePts ? n_pts : kRansacMaxTilePts;
     const int smem = ((tile_pts + 1) & ~1) * 16;
     const int hpt = g_ransac_hpt.load();
-    const bool packed = g_ransac_packed.load() != 0;
+    const int mode = g_ransac_packed.load();
     const int threads = g_ransac_threads.load();
     using Kern = void (*)(const float4*, int64_t, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
                           uint32_t, uint32_t, uint64_t, float, unsigned long long*);
-    Kern kern;
-    if (threads == 512)
-        kern = packed ? (hpt == 4 ? k_ransac_aca<4, true, 512> : k_ransac_aca<2, true, 512>)
-                      : (hpt == 4 ? k_ransac_aca<4, false, 512> : k_ransac_aca<2, false, 512>);
-    else if (threads == 384)
-        kern = packed ? (hpt == 4 ? k_ransac_aca<4, true, 384> : k_ransac_aca<2, true, 384>)
-                      : (hpt == 4 ? k_ransac_aca<4, false, 384> : k_ransac_aca<2, false, 384>);
-    else
-        kern = packed ? (hpt == 4 ? k_ransac_aca<4, true, 256> : k_ransac_aca<2, true, 256>)
-                      : (hpt == 4 ? k_ransac_aca<4, false, 256> : k_ransac_aca<2, false, 256>);
+#define SKS_RANSAC_PICK(T)                                                                        \
+    (mode == 2 ? (hpt == 4 ? k_ransac_aca<4, 2, T> : k_ransac_aca<2, 2, T>)                       \
+     : mode == 1 ? (hpt == 4 ? k_ransac_aca<4, 1, T> : k_ransac_aca<2, 1, T>)                     \
+                 : (hpt == 4 ? k_ransac_aca<4, 0, T> : k_ransac_aca<2, 0, T>))
+    const Kern kern = threads == 512 ? SKS_RANSAC_PICK(512)
+                    : threads == 384 ? SKS_RANSAC_PICK(384) : SKS_RANSAC_PICK(256);
+#undef SKS_RANSAC_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     // chunk: enough hypotheses per CTA to amortise the tile load, enough CTAs
@@ -504,8 +501,9 @@ int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int pack
         return SKS_ERR_INVALID_ARG;
     g_ransac_hpt.store(hyps_per_thread);
     g_ransac_rounds.store(rounds_per_cta);
-    g_ransac_packed.store(packed & 1);
-    const int t = packed >> 1;                       // bits 1.. select the CTA size
+    if ((packed & 3) == 3) return SKS_ERR_INVALID_ARG;
+    g_ransac_packed.store(packed & 3);
+    const int t = packed >> 2;                       // bits 2.. select the CTA size
     g_ransac_threads.store(t == 1 ? 384 : t == 2 ? 512 : 256);
     return SKS_OK;
 }

@@ -6,15 +6,18 @@
 // bit-exact fp32 ACA (MOD/ACA_SKS.cpp:24-102).  The scoring rule is this
 // project's definition and is mirrored operation for operation by
 // oracle_ransac_count_f32 (oracle/sks_oracle.c) so inlier counts are bit-exact:
-//     u = fma(h0,x,fma(h1,y,h2));  v = fma(h3,x,fma(h4,y,h5));
-//     w = fma(h6,x,fma(h7,y,h8));
-//     du = fma(X,w,-u); dv = fma(Y,w,-v); e = fma(dv,dv,du*du)
-//     acc = fma(-thr2, w*w, e);  inlier <=> acc < 0
-//   (division-free forward transfer error |proj(x) - X|^2 < thr2, both sides
-//   multiplied by w^2).  On the GPU "acc < 0" is read off the sign bit and added
-//   to the count with one integer instruction: acc is never -0 (e >= +0 and an
-//   exact cancellation rounds to +0) and a NaN acc is the canonical positive NaN
-//   on NVIDIA hardware, so the sign bit is exactly the IEEE comparison the
+//     it = 1/sqrt(thr2);  g_k = h_k*it (k<6), g_6..8 = h_6..8;  Xs = X*it, Ys = Y*it
+//     u = fma(g0,x,fma(g1,y,g2));  v = fma(g3,x,fma(g4,y,g5));
+//     w = fma(g6,x,fma(g7,y,g8));
+//     du = fma(-Xs,w,u); dv = fma(-Ys,w,v); e = fma(dv,dv,du*du)
+//     acc = fma(-w, w, e);  inlier <=> acc < 0
+//   (division-free forward transfer error |proj(x) - X|^2 < thr^2, both sides
+//   multiplied by (w/thr)^2; the threshold is folded into the operands once per
+//   hypothesis and once per match, which leaves 11 FP32 operations per hypothesis
+//   x match instead of 12).  On the GPU "acc < 0" is read off the sign bit and
+//   added to the count with one integer instruction: acc is never -0 (e >= +0 and
+//   an exact cancellation rounds to +0) and a NaN acc is the canonical positive
+//   NaN on NVIDIA hardware, so the sign bit is exactly the IEEE comparison the
 //   oracle evaluates.
 //
 // Mapping: a CTA owns one image pair and a contiguous chunk of hypothesis ids.
@@ -23,7 +26,7 @@
 // pairs; every thread then carries HPT hypotheses in registers and walks the
 // tile with warp-uniform (broadcast) 16-byte shared loads, scoring two matches
 // per instruction with sm_100a's packed FFMA2 / FMUL2, so the inner loop is pure
-// FP32 pipe work: 12 packed FP32 + 2 LEA.HI per two hypothesis x match
+// FP32 pipe work: 10 packed FP32 + 2 FFMA + 2 LEA.HI per two hypothesis x match
 // evaluations.  The best (count, lowest id) is reduced with warp shuffles, then
 // one 64-bit atomicMax per CTA.  Bound: FP32 pipe, more precisely its register
 // operand bandwidth (tools/ubench/fma_peak.cu: an FFMA2 reading three fresh
@@ -45,9 +48,13 @@
 #ifndef SKS_RANSAC_SCALAR_RESID
 #define SKS_RANSAC_SCALAR_RESID 0
 #endif
-#ifndef SKS_RANSAC_STAGED
-#define SKS_RANSAC_STAGED 0      // 1 = stage-major volatile-asm scorer (kept for the record: ptxas
-                                 // re-interleaves it, measured 70 % vs 74.6 % for the plain form)
+#ifndef SKS_RANSAC_TAIL
+#define SKS_RANSAC_TAIL 1        // last step of the packed scorer: 0 = two scalar FFMA(-w,w,e);
+                                 // 1 = sign flip of w on the ALU pipe + one FFMA2; 2 = FMUL2 + compare
+#endif
+#ifndef SKS_RANSAC_H8_ONE
+#define SKS_RANSAC_H8_ONE 0      // 1 = packed scorer uses the literal 1.0f for h33 (every hypothesis is
+                                 // h33-normalised, MOD/ACA_SKS.cpp:98, so the bits are the same)
 #endif
 
 namespace sksb {
@@ -83,33 +90,54 @@ __device__ __forceinline__ void ransac_hypothesis(const float4* __restrict__ cor
     aca_solve<float>(s, t, h, true);
 }
 
-// 1 if the match is an inlier of h, else 0 (sign bit of acc, see header)
-__device__ __forceinline__ uint32_t ransac_inlier(const float (&h)[9], const float4 c, float thr2)
+// 1/thr, the factor folded into hypotheses and matches (IEEE sqrt and divide)
+__device__ __forceinline__ float ransac_inv_thr(float thr2)
 {
-    const float u = __fmaf_rn(h[0], c.x, __fmaf_rn(h[1], c.y, h[2]));
-    const float v = __fmaf_rn(h[3], c.x, __fmaf_rn(h[4], c.y, h[5]));
-    const float w = __fmaf_rn(h[6], c.x, __fmaf_rn(h[7], c.y, h[8]));
-    const float du = __fmaf_rn(c.z, w, -u);
-    const float dv = __fmaf_rn(c.w, w, -v);
+    return __fdiv_rn(1.0f, __fsqrt_rn(thr2));
+}
+
+// g = h with rows 1-2 scaled by 1/thr (once per hypothesis)
+__device__ __forceinline__ void ransac_scale_h(float (&h)[9], float it)
+{
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        h[k] = __fmul_rn(h[k], it);
+}
+
+// 1 if the match c = (x, y, -Xs, -Ys) -- target already scaled by 1/thr and negated
+// (an exact operation) -- is an inlier of the scaled hypothesis g, else 0 (sign bit
+// of acc, see header)
+__device__ __forceinline__ uint32_t ransac_inlier(const float (&g)[9], const float4 c)
+{
+    const float u = __fmaf_rn(g[0], c.x, __fmaf_rn(g[1], c.y, g[2]));
+    const float v = __fmaf_rn(g[3], c.x, __fmaf_rn(g[4], c.y, g[5]));
+    const float w = __fmaf_rn(g[6], c.x, __fmaf_rn(g[7], c.y, g[8]));
+    const float du = __fmaf_rn(c.z, w, u);
+    const float dv = __fmaf_rn(c.w, w, v);
     const float e = __fmaf_rn(dv, dv, __fmul_rn(du, du));
-    const float acc = __fmaf_rn(-thr2, __fmul_rn(w, w), e);
+    const float acc = __fmaf_rn(-w, w, e);
     return __float_as_uint(acc) >> 31;
 }
 
 // Packed form for sm_100a's 2-wide FP32 instructions (FFMA2 / FMUL2): the same
-// test on TWO matches at once.  p0 = (x0,x1,y0,y1), p1 = (-X0,-X1,-Y0,-Y1) is the
-// pair layout the kernel rewrites the shared-memory tile into; h[k] = (h_k,h_k).
-// Bit-identical to two ransac_inlier calls: each half is an IEEE fused
-// multiply-add, u - X*w is the exact negation of X*w - u (its square is the
-// same).
-__device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&h)[9], const float4 p0,
-                                                   const float4 p1, const float2 nthr2)
+// test on TWO matches at once.  p0 = (x0,x1,y0,y1), p1 = (-Xs0,-Xs1,-Ys0,-Ys1) is
+// the pair layout the kernel rewrites the shared-memory tile into; g[k] =
+// (g_k,g_k).  Bit-identical to two ransac_inlier calls: each half is an IEEE
+// fused multiply-add and (-X)*it is the exact negation of X*it.  The last step
+// needs a negated operand, which only the scalar FFMA has, so it is two FFMAs
+// (two pipe cycles, where FMUL2 + FFMA2 took four).
+__device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&g)[9], const float4 p0,
+                                                   const float4 p1)
 {
     const float2 x = make_float2(p0.x, p0.y), y = make_float2(p0.z, p0.w);
     const float2 nX = make_float2(p1.x, p1.y), nY = make_float2(p1.z, p1.w);
-    const float2 u = __ffma2_rn(h[0], x, __ffma2_rn(h[1], y, h[2]));
-    const float2 v = __ffma2_rn(h[3], x, __ffma2_rn(h[4], y, h[5]));
-    const float2 w = __ffma2_rn(h[6], x, __ffma2_rn(h[7], y, h[8]));
+    const float2 u = __ffma2_rn(g[0], x, __ffma2_rn(g[1], y, g[2]));
+    const float2 v = __ffma2_rn(g[3], x, __ffma2_rn(g[4], y, g[5]));
+#if SKS_RANSAC_H8_ONE
+    const float2 w = __ffma2_rn(g[6], x, __ffma2_rn(g[7], y, make_float2(1.0f, 1.0f)));
+#else
+    const float2 w = __ffma2_rn(g[6], x, __ffma2_rn(g[7], y, g[8]));
+#endif
 #if SKS_RANSAC_SCALAR_RESID
     // residuals as four scalar FFMAs: a 3-pair FFMA2 needs six register reads (three
     // cycles), whereas scalar FFMAs with -X / -Y served by the reuse cache run at full rate
@@ -120,72 +148,44 @@ __device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&h)[9], const f
     const float2 dv = __ffma2_rn(nY, w, v);
 #endif
     const float2 e = __ffma2_rn(dv, dv, __fmul2_rn(du, du));
-    const float2 acc = __ffma2_rn(nthr2, __fmul2_rn(w, w), e);
+#if SKS_RANSAC_TAIL == 0
+    const float ax = __fmaf_rn(-w.x, w.x, e.x);
+    const float ay = __fmaf_rn(-w.y, w.y, e.y);
+    return (__float_as_uint(ax) >> 31) + (__float_as_uint(ay) >> 31);
+#elif SKS_RANSAC_TAIL == 1
+    const float2 nw = make_float2(__uint_as_float(__float_as_uint(w.x) ^ 0x80000000u),
+                                  __uint_as_float(__float_as_uint(w.y) ^ 0x80000000u));
+    const float2 acc = __ffma2_rn(nw, w, e);
     return (__float_as_uint(acc.x) >> 31) + (__float_as_uint(acc.y) >> 31);
+#else
+    const float2 w2 = __fmul2_rn(w, w);    // exact products: e < w*w is the same predicate as
+    return (e.x < w2.x ? 1u : 0u) + (e.y < w2.y ? 1u : 0u);   // fma(-w,w,e) < 0 only up to rounding
+#endif
 }
 
-// ---- stage-major packed scorer ------------------------------------------------
-// On sm_100 an FFMA2 may read two registers per bank (even/odd) at full rate; a
-// third costs a cycle (tools/ubench/fma_peak.cu: 84 instead of 122 FMA/clk/SM).
-// h.F32 x pair + pair is five reads, so it only runs at full rate when the match
-// pair comes from the operand-reuse cache, i.e. when consecutive instructions
-// share it in the same source slot.  The block below therefore issues the work
-// for one match pair and all HPT hypotheses stage by stage -- all y-FMAs, all
-// x-FMAs, all residual FMAs -- as volatile asm so that order reaches ptxas intact.
-__device__ __forceinline__ unsigned long long pk2(float2 v)
+// Second packed form: TWO HYPOTHESES per instruction, one match.  g[k] = (gA_k, gB_k)
+// are natural register pairs and the match scalars enter as broadcast operands
+// (SASS: Rn.F32), so no FFMA2 reads more than five registers (pair, scalar, pair)
+// and consecutive instructions share the scalar through the operand-reuse cache;
+// the match-pair form above needs six for its residuals (three pairs), which costs
+// a third pipe cycle (tools/ubench/fma_peak.cu).  c = (x, y, -Xs, -Ys).
+__device__ __forceinline__ void ransac_inlier_hp(const float2 (&g)[9], const float4 c,
+                                                 uint32_t& cnt_a, uint32_t& cnt_b)
 {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
-    return r;
-}
-__device__ __forceinline__ unsigned long long ffma2v(unsigned long long a, unsigned long long b,
-                                                     unsigned long long c)
-{
-    unsigned long long d;
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ unsigned long long fmul2v(unsigned long long a, unsigned long long b)
-{
-    unsigned long long d;
-    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
-template <int HPT>
-__device__ __forceinline__ void ransac_score_pair_staged(const unsigned long long (&h)[HPT][9],
-                                                         const float4 p0, const float4 p1,
-                                                         unsigned long long nthr2,
-                                                         uint32_t (&cnt)[HPT])
-{
-    const unsigned long long x = pk2(make_float2(p0.x, p0.y)), y = pk2(make_float2(p0.z, p0.w));
-    const unsigned long long nX = pk2(make_float2(p1.x, p1.y)), nY = pk2(make_float2(p1.z, p1.w));
-    unsigned long long t[HPT][3];
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)          // stage 1: y shared in slot B
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            t[j][r] = ffma2v(h[j][3 * r + 1], y, h[j][3 * r + 2]);
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)          // stage 2: x shared in slot B -> u, v, w
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            t[j][r] = ffma2v(h[j][3 * r], x, t[j][r]);
-    unsigned long long du[HPT], dv[HPT];
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)          // stage 3: -X shared in slot A, then -Y
-        du[j] = ffma2v(nX, t[j][2], t[j][0]);
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)
-        dv[j] = ffma2v(nY, t[j][2], t[j][1]);
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) {        // stage 4: at most two fresh pairs each
-        const unsigned long long e0 = fmul2v(du[j], du[j]);
-        const unsigned long long e = ffma2v(dv[j], dv[j], e0);
-        const unsigned long long w2 = fmul2v(t[j][2], t[j][2]);
-        const unsigned long long acc = ffma2v(nthr2, w2, e);
-        cnt[j] += (uint32_t)((acc >> 31) & 1ull) + (uint32_t)(acc >> 63);
-    }
+    const float2 x = make_float2(c.x, c.x), y = make_float2(c.y, c.y);
+    const float2 nX = make_float2(c.z, c.z), nY = make_float2(c.w, c.w);
+    const float2 u = __ffma2_rn(g[0], x, __ffma2_rn(g[1], y, g[2]));
+    const float2 v = __ffma2_rn(g[3], x, __ffma2_rn(g[4], y, g[5]));
+    const float2 w = __ffma2_rn(g[6], x, __ffma2_rn(g[7], y, g[8]));
+    const float2 du = __ffma2_rn(nX, w, u);
+    const float2 dv = __ffma2_rn(nY, w, v);
+    const float2 e = __ffma2_rn(dv, dv, __fmul2_rn(du, du));
+    // -w: ptxas folds the sign flip into FFMA2's operand negation
+    const float2 nw = make_float2(__uint_as_float(__float_as_uint(w.x) ^ 0x80000000u),
+                                  __uint_as_float(__float_as_uint(w.y) ^ 0x80000000u));
+    const float2 acc = __ffma2_rn(nw, w, e);
+    cnt_a += __float_as_uint(acc.x) >> 31;
+    cnt_b += __float_as_uint(acc.y) >> 31;
 }
 
 __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_t hyp)
@@ -195,9 +195,10 @@ __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_
 
 // grid = (chunks_per_pair, n_pairs); each CTA scores hypothesis ids
 // [hyp_begin + chunk*chunk_size, +chunk_size) ∩ [hyp_begin, hyp_begin+hyp_count)
-// kRansacHpt: hypotheses carried per thread per round.  PACKED: score two matches
-// per instruction with FFMA2/FMUL2 (the tile is re-laid out in pairs on arrival).
-template <int kRansacHpt, bool PACKED, int kRansacThreads>
+// kRansacHpt: hypotheses carried per thread per round.  MODE 0: scalar FFMA scorer;
+// 1: two matches per FFMA2/FMUL2 (the tile is re-laid out in pairs on arrival);
+// 2: two hypotheses per FFMA2/FMUL2 (tile stays one match per 16 bytes).
+template <int kRansacHpt, int MODE, int kRansacThreads>
 __global__ void __launch_bounds__(kRansacThreads)
 k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, int32_t tile_pts,
              const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
@@ -234,10 +235,14 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
         load_tile(0);
     bool resident = false;   // single tile stays in shared memory for all rounds
 
+    constexpr bool PACKED = (MODE == 1);
+    constexpr bool HYPPAIR = (MODE == 2);
+    static_assert(!HYPPAIR || kRansacHpt % 2 == 0, "hypothesis pairs");
+    const float it = ransac_inv_thr(thr2);
     unsigned long long best = 0ull;
     for (uint32_t base = c_lo; base < c_hi; base += kRansacThreads * kRansacHpt) {
         float h[kRansacHpt][9];
-        float2 h2[PACKED ? kRansacHpt : 1][9];
+        float2 h2[PACKED ? kRansacHpt : HYPPAIR ? kRansacHpt / 2 : 1][9];
         uint32_t cnt[kRansacHpt], hyp[kRansacHpt];
         bool live[kRansacHpt];
 #pragma unroll
@@ -248,6 +253,7 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
             uint32_t idx[4];
             ransac_sample(key, pair, hyp[j], samples, hyp_stride, (uint32_t)n_pts, idx);
             ransac_hypothesis(corr_pair, idx, h[j]);
+            ransac_scale_h(h[j], it);
             cnt[j] = 0;
             if constexpr (PACKED) {
 #pragma unroll
@@ -255,16 +261,13 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
                     h2[j][k] = make_float2(h[j][k], h[j][k]);
             }
         }
-        const float2 nthr2 = make_float2(-thr2, -thr2);
-        unsigned long long hq[PACKED ? kRansacHpt : 1][9];
-        if constexpr (PACKED) {
+        if constexpr (HYPPAIR) {
 #pragma unroll
-            for (int j = 0; j < kRansacHpt; ++j)
+            for (int j = 0; j < kRansacHpt / 2; ++j)
 #pragma unroll
                 for (int k = 0; k < 9; ++k)
-                    hq[j][k] = pk2(h2[j][k]);
+                    h2[j][k] = make_float2(h[2 * j][k], h[2 * j + 1][k]);
         }
-        const unsigned long long nthr2q = pk2(nthr2);
         for (int tl = 0; tl < n_tiles; ++tl) {
             const int lo = tl * tile_pts;
             const int np = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
@@ -273,19 +276,25 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
                 phase ^= 1;
                 resident = (n_tiles == 1);
                 if constexpr (PACKED) {
-                    // re-lay the freshly landed AoS tile out in pairs, in place:
-                    // (x0,x1,y0,y1)(-X0,-X1,-Y0,-Y1); an odd tail is padded with a
-                    // NaN target that can never be an inlier
+                    // re-lay the freshly landed AoS tile out in pairs, in place, with the
+                    // targets scaled by 1/thr: (x0,x1,y0,y1)(-Xs0,-Xs1,-Ys0,-Ys1); an odd
+                    // tail is padded with a NaN target that can never be an inlier
                     const float qnan = __int_as_float(0x7fffffff);
                     for (int p = tid; 2 * p < np; p += kRansacThreads) {
                         const float4 a = tile[2 * p];
                         const float4 b = (2 * p + 1 < np) ? tile[2 * p + 1]
                                                           : make_float4(0.f, 0.f, qnan, qnan);
                         tile[2 * p] = make_float4(a.x, b.x, a.y, b.y);
-                        tile[2 * p + 1] = make_float4(-a.z, -b.z, -a.w, -b.w);
+                        tile[2 * p + 1] = make_float4(__fmul_rn(-a.z, it), __fmul_rn(-b.z, it),
+                                                      __fmul_rn(-a.w, it), __fmul_rn(-b.w, it));
                     }
-                    __syncthreads();
+                } else {
+                    for (int p = tid; p < np; p += kRansacThreads) {   // (x, y, -Xs, -Ys)
+                        const float4 a = tile[p];
+                        tile[p] = make_float4(a.x, a.y, __fmul_rn(-a.z, it), __fmul_rn(-a.w, it));
+                    }
                 }
+                __syncthreads();
             }
             if constexpr (PACKED) {
                 const int npair = (np + 1) >> 1;
@@ -295,29 +304,44 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
 #pragma unroll
                     for (int k = 0; k < 2 * SKS_RANSAC_UNROLL; ++k)
                         c[k] = tile[2 * i + k];   // warp-uniform address: broadcast
-#if SKS_RANSAC_STAGED
-#pragma unroll
-                    for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
-                        ransac_score_pair_staged<kRansacHpt>(hq, c[2 * k], c[2 * k + 1], nthr2q, cnt);
-#elif SKS_RANSAC_HYP_MAJOR
+#if SKS_RANSAC_HYP_MAJOR
 #pragma unroll
                     for (int j = 0; j < kRansacHpt; ++j)
 #pragma unroll
                         for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
-                            cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1], nthr2);
+                            cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1]);
 #else
 #pragma unroll
                     for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
 #pragma unroll
                         for (int j = 0; j < kRansacHpt; ++j)
-                            cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1], nthr2);
+                            cnt[j] += ransac_inlier2(h2[j], c[2 * k], c[2 * k + 1]);
 #endif
                 }
                 for (; i < npair; ++i) {
                     const float4 c0 = tile[2 * i], c1 = tile[2 * i + 1];
 #pragma unroll
                     for (int j = 0; j < kRansacHpt; ++j)
-                        cnt[j] += ransac_inlier2(h2[j], c0, c1, nthr2);
+                        cnt[j] += ransac_inlier2(h2[j], c0, c1);
+                }
+            } else if constexpr (HYPPAIR) {
+                int i = 0;
+                for (; i + SKS_RANSAC_UNROLL <= np; i += SKS_RANSAC_UNROLL) {
+                    float4 c[SKS_RANSAC_UNROLL];
+#pragma unroll
+                    for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
+                        c[k] = tile[i + k];   // warp-uniform address: broadcast
+#pragma unroll
+                    for (int k = 0; k < SKS_RANSAC_UNROLL; ++k)
+#pragma unroll
+                        for (int j = 0; j < kRansacHpt / 2; ++j)
+                            ransac_inlier_hp(h2[j], c[k], cnt[2 * j], cnt[2 * j + 1]);
+                }
+                for (; i < np; ++i) {
+                    const float4 c = tile[i];
+#pragma unroll
+                    for (int j = 0; j < kRansacHpt / 2; ++j)
+                        ransac_inlier_hp(h2[j], c, cnt[2 * j], cnt[2 * j + 1]);
                 }
             } else {
                 int i = 0;
@@ -330,13 +354,13 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
                         for (int j = 0; j < kRansacHpt; ++j)
-                            cnt[j] += ransac_inlier(h[j], c[k], thr2);
+                            cnt[j] += ransac_inlier(h[j], c[k]);
                 }
                 for (; i < np; ++i) {
                     const float4 c = tile[i];
 #pragma unroll
                     for (int j = 0; j < kRansacHpt; ++j)
-                        cnt[j] += ransac_inlier(h[j], c, thr2);
+                        cnt[j] += ransac_inlier(h[j], c);
                 }
             }
             if (n_tiles > 1) {   // stream the next tile (wraps for the next round)
@@ -398,13 +422,18 @@ k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
         total = 0;
     }
     __syncthreads();
+    const float it = ransac_inv_thr(thr2);
     float h[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
         h[k] = hs[k];
+    ransac_scale_h(h, it);
     uint32_t mine = 0;
     for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
-        const uint32_t in = ransac_inlier(h, __ldg(corr_pair + i), thr2);
+        float4 c = __ldg(corr_pair + i);
+        c.z = __fmul_rn(-c.z, it);
+        c.w = __fmul_rn(-c.w, it);
+        const uint32_t in = ransac_inlier(h, c);
         mine += in;
         if (inlier_mask != nullptr)
             inlier_mask[(size_t)pair * n_pts + i] = in ? 1 : 0;

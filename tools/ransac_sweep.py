@@ -12,10 +12,7 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "tools", "_variants")
 VARIANTS = {}
 for u in (2, 4, 8):
-    for hm in (0, 1):
-        for sr in (0, 1):
-            VARIANTS[f"rs_u{u}_hm{hm}_sr{sr}"] = [f"-DSKS_RANSAC_UNROLL={u}", f"-DSKS_RANSAC_HYP_MAJOR={hm}",
-                                                 f"-DSKS_RANSAC_SCALAR_RESID={sr}", "-DSKS_RANSAC_STAGED=0"]
+    VARIANTS[f"rs_u{u}"] = [f"-DSKS_RANSAC_UNROLL={u}"]
 
 if "--build" in sys.argv:
     from sks_homography_b200 import build as b
@@ -38,8 +35,8 @@ ref = api.ransac_keys(corr, n_hyp, 11, 2.25)
 st = torch.cuda.current_stream().cuda_stream
 for path in sorted(glob.glob(os.path.join(VDIR, "libsks_cuda_rs_*.so"))):
     L = _lib.SksCuda(path)
-    for hpt in (2, 4):
-        L.c.sks_cuda_set_ransac_tuning(hpt, 8 if hpt == 2 else 4, 1)
+    for mode, hpt, thr in [(1, 2, 0), (2, 2, 0), (2, 4, 0), (2, 2, 1), (2, 4, 1), (2, 2, 2), (2, 4, 2)]:
+        L.c.sks_cuda_set_ransac_tuning(hpt, 8 if hpt == 2 else 4, mode | (thr << 2))
         keys = torch.zeros(P, dtype=torch.int64, device=dev)
         run = lambda: L.check(L.c.sks_cuda_ransac_aca_f32(corr.data_ptr(), P, n_pts, None, n_hyp, 0, n_hyp, 11,
                                                           2.25, keys.data_ptr(), st), "ransac")
@@ -51,5 +48,6 @@ for path in sorted(glob.glob(os.path.join(VDIR, "libsks_cuda_rs_*.so"))):
             run()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        tf = P * n_hyp * (97 + 22.0 * n_pts) / ms / 1e9
-        print(f"{os.path.basename(path):32s} hpt={hpt} {ms:8.3f} ms  {tf:6.2f} TFLOP/s  {tf / 74.45:.3f} of peak  same_keys={ok}", flush=True)
+        tf = P * n_hyp * (103 + 21.0 * n_pts) / ms / 1e9
+        print(f"{os.path.basename(path):24s} mode={mode} hpt={hpt} threads={(256, 384, 512)[thr]} {ms:8.3f} ms  "
+              f"{tf:6.2f} TFLOP/s  {tf / 74.45:.3f} of peak  same_keys={ok}", flush=True)
