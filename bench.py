@@ -45,6 +45,10 @@ WORKLOADS = {
     "aca_f64": ("aca", "f64", 200, 25, 1),
     "sks_f64": ("sks", "f64", 200, 25, 1),     # BASELINE configs[3]
     "rect_f32": ("rect", "f32", 68, 26, 0),    # BASELINE configs[2] per-GPU shard at 4 GPUs
+    # competitor solver in the same harness; dist 1 because GE has no
+    # pivoting and fails on the axis-aligned source squares of dist 0
+    "ge_f32": ("ge", "f32", 100, 26, 1),
+    "ge_f64": ("ge", "f64", 200, 25, 1),
 }
 
 
@@ -129,6 +133,8 @@ def run_reference(args):
     o = Oracle()
     kind = "reference"
     try:
+        if solver == "ge" and dt == "f64":
+            raise LookupError("the reference's C++ GE is fp32 only")
         ref = RefLib()
         threads = ref.hardware_threads()
         run = lambda s, t, out: ref.solve(solver, s, t, threads=threads, out=out)
@@ -151,8 +157,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dt, "data": "synthetic",
-        "config": {"workload": f"{args.workload} AoS h33-normalised, reference C++ on host cores, "
-                               f"step = 2^{args.ref_log2n} distinct quadruples streamed from memory",
+        "config": {"workload": f"batched {solver.upper()} {dt} 2^{args.log2n or log2n} quadruples per GPU, AOS in/out, "
+                               f"h33-normalised -- reference C++ on the host cores, each step a bounded sample "
+                               f"of 2^{args.ref_log2n} distinct quadruples streamed from memory",
                    "threads": threads, "compiler": "g++ -O2 -ffp-contract=off"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"2^{args.ref_log2n} quadruples per step x {args.steps} steps"},
@@ -340,6 +347,8 @@ def main():
         s_h, t_h = src[:S].cpu().numpy(), tar[:S].cpu().numpy()
         out = np.empty((S, 9), dtype=s_h.dtype)
         try:
+            if solver == "ge" and dt == "f64":
+                raise LookupError("the reference's C++ GE is fp32 only")
             ref = RefLib()
             threads, kind = ref.hardware_threads(), "reference"
             run = lambda: ref.solve(solver, s_h, t_h, threads=threads, out=out)
@@ -359,7 +368,8 @@ def main():
             parity = {"checked_quadruples": int(S), "mismatching_elements": int((~ok).sum())}
         cpu = {"value": S / best, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"first 2^{args.cpu_log2n} quadruples of the workload, best of 5 passes, "
-                         f"MOD/ACA_SKS.cpp g++ -O2 -ffp-contract=off, {threads} threads",
+                         f"{'MOD/GE.cpp' if solver == 'ge' else 'MOD/ACA_SKS.cpp'} g++ -O2 -ffp-contract=off"
+                         f"{'' if kind == 'reference' else ' (oracle port)'}, {threads} threads",
                "parity_gpu_vs_cpu": parity}
 
     gpu_base = None
@@ -414,14 +424,14 @@ def reference_gpu_kernels(api, dev):
         ref = RefGpuLib()
     except Exception as e:                                   # not built: report, do not fail
         return {"unavailable": str(e)[:120]}
-    out = {"kernels": "GPU_Runtime Test.cu:81-240 cal_Homo_ACA/SKS, nvcc -O3 sm_100a, block 32, "
-                      "fp64 SoA un-normalised", "rows": []}
+    out = {"kernels": "GPU_Runtime Test.cu:81-240 cal_Homo_ACA/SKS and :359-507 cal_Homo_GE, nvcc -O3 "
+                      "sm_100a, block 32, fp64 SoA un-normalised", "rows": []}
     for log2n in (20, 25):
         n = 1 << log2n
         src, tar = api.synth_quads(n, 11, 1, torch.float64, dev, layout="soa")
         H = torch.empty((9, n), dtype=torch.float64, device=dev)
         st = torch.cuda.current_stream().cuda_stream
-        for solver in ("aca", "sks"):
+        for solver in ("aca", "sks", "ge"):
             t_ref = _event_ms(lambda: ref.run(solver, src.data_ptr(), tar.data_ptr(), H.data_ptr(), n, st), 20)
             t_our = _event_ms(lambda: api.solve(solver, src, tar, result=H, normalize=False, layout="soa"), 20)
             out["rows"].append({"solver": solver, "n": n, "reference_us": 1e3 * t_ref, "ours_us": 1e3 * t_our,

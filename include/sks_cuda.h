@@ -74,6 +74,17 @@ int sks_cuda_sks_f32(const float *src, const float *tar, float *H, int64_t n, in
 int sks_cuda_sks_f64(const double *src, const double *tar, double *H, int64_t n, int layout,
                      int64_t ld, int flags, uint8_t *degenerate, void *stream);
 
+/* Competitor solver in the same harness, bit-exact to
+ * cv::runKernel_GE                       MOD/GE.hpp:9, MOD/GE.cpp:44-188 (fp32)
+ * cal_Homo_GE (SoA fp64, -fmad=false)    GPU.cu:359-507
+ * RHO Gaussian elimination, 221 flops; h33 is 1 by construction, so flags'
+ * SKS_FLAG_NORMALIZE bit makes no difference; no pivoting: an axis-aligned source
+ * square gives a non-finite result exactly as the reference does. */
+int sks_cuda_ge_f32(const float *src, const float *tar, float *H, int64_t n, int layout,
+                    int64_t ld, int flags, uint8_t *degenerate, void *stream);
+int sks_cuda_ge_f64(const double *src, const double *tar, double *H, int64_t n, int layout,
+                    int64_t ld, int flags, uint8_t *degenerate, void *stream);
+
 /* replaces ACA_rect(TargetPts, M_x, M_y, width, ratio_rec)  ML/ACA_rect.m:22-38
  *          TensorACA_rect(bs, src, tar, scale, div)         PY.py:286-309
  * tar holds the 4 target corners TL,TR,BL,BR (8 values per quadruple, the
@@ -111,6 +122,8 @@ int sks_host_aca_f32(const float *src, const float *tar, float *H, int64_t n, in
 int sks_host_aca_f64(const double *src, const double *tar, double *H, int64_t n, int flags);
 int sks_host_sks_f32(const float *src, const float *tar, float *H, int64_t n, int flags);
 int sks_host_sks_f64(const double *src, const double *tar, double *H, int64_t n, int flags);
+int sks_host_ge_f32(const float *src, const float *tar, float *H, int64_t n, int flags);
+int sks_host_ge_f64(const double *src, const double *tar, double *H, int64_t n, int flags);
 int sks_host_aca_rect_f32(const float *tar, const float *M, float mx, float my, float width,
                           float ratio, float *H, int64_t n, int flags);
 int sks_host_aca_rect_f64(const double *tar, const double *M, double mx, double my,

@@ -69,3 +69,17 @@ inline int runKernel_ACA_rect_double(double* tar, double M_x, double M_y, double
 }
 
 }  // namespace sks
+
+// The reference keeps its competitor solvers in namespace cv; the one that is
+// self-contained, RHO-GE ("C++ Codes/modules/GE.hpp":9, void return), is served by
+// the same streaming kernel (bit-exact to MOD/GE.cpp).  Define SKS_NO_CV_NAMESPACE
+// when OpenCV's own cv:: is in scope and the names would collide.
+#ifndef SKS_NO_CV_NAMESPACE
+namespace cv {
+inline int runKernel_GE(float* src, float* tar, float* result, std::int64_t n)
+{
+    return sks_host_ge_f32(src, tar, result, n, SKS_FLAG_NORMALIZE);
+}
+inline void runKernel_GE(float* src, float* tar, float* result) { (void)runKernel_GE(src, tar, result, 1); }
+}  // namespace cv
+#endif

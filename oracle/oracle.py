@@ -20,13 +20,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libsks_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsks_ref.so")
 REFGPU_SO = os.path.join(HERE, "_ref", "libsks_refgpu.so")
+REFGPU_NOFMA_SO = os.path.join(HERE, "_ref", "libsks_refgpu_nofma.so")
 REFERENCE_ROOT = "/root/reference"
 
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference checkout exists)."""
     need = force or not os.path.exists(ORACLE_SO)
-    if os.path.isdir(REFERENCE_ROOT) and not (os.path.exists(REF_SO) and os.path.exists(REFGPU_SO)):
+    if os.path.isdir(REFERENCE_ROOT) and not all(os.path.exists(f) for f in (REF_SO, REFGPU_SO, REFGPU_NOFMA_SO)):
         need = True
     if need:
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True,
@@ -155,7 +156,8 @@ class RefLib:
         return int(self.lib.ref_hardware_threads())
 
     def solve(self, solver: str, src, tar, threads: int = 1, out=None) -> np.ndarray:
-        """solver in {aca, sks}; always h33-normalised (MOD/ACA_SKS.cpp:94-98)."""
+        """solver in {aca, sks} (fp32/fp64) or ge (fp32 only, MOD/GE.cpp); always h33-normalised
+        (MOD/ACA_SKS.cpp:94-98)."""
         dt = np.asarray(src).dtype
         src, tar = _c(src, dt).reshape(-1, 8), _c(tar, dt).reshape(-1, 8)
         n = src.shape[0]
@@ -166,20 +168,28 @@ class RefLib:
 
 
 class RefGpuLib:
-    """The reference's own CUDA kernels (GPU.cu:81-240, extracted and compiled for
-    sm_100a at build time by oracle/Makefile) behind their reference launch shape
-    <<<ceil(N/32),32>>>: fp64, SoA, un-normalised.  Perf comparator only."""
+    """The reference's own CUDA kernels (GPU.cu:81-240 cal_Homo_ACA/SKS, :359-507
+    cal_Homo_GE, extracted and compiled for sm_100a at build time by oracle/Makefile)
+    behind their reference launch shape <<<ceil(N/32),32>>>: fp64, SoA, un-normalised.
+    Default build (FMA contraction on, as the reference ships): perf comparator only.
+    ``nofma=True`` loads the -fmad=false build, whose rounding is that of the
+    reference's C++: a GPU-side parity pin for our SoA fp64 kernels."""
 
-    def __init__(self):
-        if not os.path.exists(REFGPU_SO):
+    def __init__(self, nofma: bool = False):
+        so = REFGPU_NOFMA_SO if nofma else REFGPU_SO
+        if not os.path.exists(so):
             build()
-        if not os.path.exists(REFGPU_SO):
-            raise FileNotFoundError(REFGPU_SO)
-        self.lib = C.CDLL(REFGPU_SO)
-        for name in ("refgpu_aca_f64", "refgpu_sks_f64"):
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
+        self.lib = C.CDLL(so)
+        for name in ("refgpu_aca_f64", "refgpu_sks_f64", "refgpu_ge_f64"):
             fn = getattr(self.lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+
+    @staticmethod
+    def available(nofma: bool = False) -> bool:
+        return os.path.exists(REFGPU_NOFMA_SO if nofma else REFGPU_SO) or os.path.isdir(REFERENCE_ROOT)
 
     def run(self, solver: str, d_src: int, d_tar: int, d_H: int, n: int, stream: int) -> None:
         rc = getattr(self.lib, f"refgpu_{solver}_f64")(d_src, d_tar, d_H, n, stream)

@@ -2,7 +2,8 @@
 // C++ solvers, linked with "C++ Codes/modules/ACA_SKS.cpp" compiled IN PLACE
 // from /root/reference by oracle/Makefile into oracle/_ref/libsks_ref.so.
 // No reference source is copied into this repository; this file only declares
-// the four entry points (MOD/ACA_SKS.hpp:17-20) and loops over them the way
+// the four entry points (MOD/ACA_SKS.hpp:17-20) plus the competitor cv::runKernel_GE
+// (MOD/GE.hpp:9, from MOD/GE.cpp compiled the same way) and loops over them the way
 // the reference's CPU harness does (CPU/main.cpp:87-114), but over DISTINCT
 // quadruples streamed from memory and optionally on several host threads.
 //
@@ -19,6 +20,18 @@ int runKernel_ACA_double(double* src, double* tar, double* result);
 int runKernel_SKS(float* src, float* tar, float* result);
 int runKernel_SKS_double(double* src, double* tar, double* result);
 }  // namespace sks
+namespace cv {
+void runKernel_GE(float* src, float* tar, float* result);   // MOD/GE.hpp:9 (RHO-GE competitor, fp32 only)
+}
+
+namespace {
+
+int ge_as_int(float* s, float* t, float* r)
+{
+    cv::runKernel_GE(s, t, r);
+    return 0;
+}
+}  // namespace
 
 namespace {
 
@@ -65,6 +78,10 @@ void ref_sks_f32(const float* s, const float* t, float* H, int64_t n, int thread
 void ref_sks_f64(const double* s, const double* t, double* H, int64_t n, int threads)
 {
     run_batch<double, sks::runKernel_SKS_double>(s, t, H, n, threads);
+}
+void ref_ge_f32(const float* s, const float* t, float* H, int64_t n, int threads)
+{
+    run_batch<float, ge_as_int>(s, t, H, n, threads);
 }
 
 }  // extern "C"

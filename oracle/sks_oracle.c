@@ -14,6 +14,11 @@
  *     and to golden vectors obtained by executing
  *     "PyTorch Codes/Modules_Runtime_Test.py":296-302 on torch-CPU
  *     (tests/golden/make_golden.py).  No C++ version exists in the reference.
+ *   RHO-GE (competitor solver): fp32 PINNED -- bit-compared
+ *     against the reference's MOD/GE.cpp compiled in place (same _ref library);
+ *     fp64 is the same type-generic body (the reference's only fp64 GE is its
+ *     FMA-contracted CUDA kernel GPU.cu:359-507; recompiled with -fmad=false into
+ *     oracle/_ref/libsks_refgpu.so it is bit-compared on the GPU box).
  *   RANSAC scoring: PARITY UNPINNED -- the reference has no inlier test or model
  *     selection (only the sampler precedent GPU.cu:52-78).  Hypotheses are the
  *     pinned ACA; the scoring rule below is this project's own definition.
@@ -52,6 +57,8 @@ DEF_BATCH(oracle_aca_f32, float, oracle_aca_one_f32)
 DEF_BATCH(oracle_aca_f64, double, oracle_aca_one_f64)
 DEF_BATCH(oracle_sks_f32, float, oracle_sks_one_f32)
 DEF_BATCH(oracle_sks_f64, double, oracle_sks_one_f64)
+DEF_BATCH(oracle_ge_f32, float, oracle_ge_one_f32)
+DEF_BATCH(oracle_ge_f64, double, oracle_ge_one_f64)
 
 /* M == NULL: one shared rectangle corner (mx,my); else per-sample M[n][2]
  * (PyTorch Codes/Modules_Runtime_Test.py:302 reads M per sample while

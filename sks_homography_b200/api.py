@@ -102,6 +102,14 @@ def runKernel_SKS_double(src, tar, result=None, **kw):
     return solve("sks", src, tar, result, **kw)
 
 
+def runKernel_GE(src, tar, result=None, **kw):
+    """Competitor solver cv::runKernel_GE (MOD/GE.hpp:9): RHO Gaussian elimination,
+    fp32 in the reference; float64 tensors run the same elimination in fp64
+    (the arithmetic of the reference's CUDA kernel cal_Homo_GE, GPU.cu:359-507)."""
+    _check_pair(src, tar, src.dtype)
+    return solve("ge", src, tar, result, **kw)
+
+
 def aca_rect(tar: torch.Tensor, width: float, ratio: float, M_x: float = 0.0, M_y: float = 0.0,
              M: torch.Tensor | None = None, result: torch.Tensor | None = None,
              normalize: bool = True, layout: str = "aos",

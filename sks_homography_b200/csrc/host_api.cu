@@ -312,6 +312,14 @@ int sks_host_sks_f64(const double* src, const double* tar, double* H, int64_t n,
 {
     return host_general<double>(sks_cuda_sks_f64, src, tar, H, n, flags);
 }
+int sks_host_ge_f32(const float* src, const float* tar, float* H, int64_t n, int flags)
+{
+    return host_general<float>(sks_cuda_ge_f32, src, tar, H, n, flags);
+}
+int sks_host_ge_f64(const double* src, const double* tar, double* H, int64_t n, int flags)
+{
+    return host_general<double>(sks_cuda_ge_f64, src, tar, H, n, flags);
+}
 int sks_host_aca_rect_f32(const float* tar, const float* M, float mx, float my, float width,
                           float ratio, float* H, int64_t n, int flags)
 {

@@ -11,6 +11,8 @@
 //                     cal_Homo_SKS (no normalise)   GPU.cu:153-240
 //   aca_rect_solve <- ACA_rect                      ML/ACA_rect.m:25-36
 //                     TensorACA_rect                PY.py:296-302
+//   ge_solve       <- cv::runKernel_GE (competitor) MOD/GE.cpp:44-188
+//                     cal_Homo_GE (fp64)            GPU.cu:359-507
 #pragma once
 #include "strict.cuh"
 
@@ -231,6 +233,106 @@ __device__ __forceinline__ void aca_rect_solve(const T (&t)[8], T mx_, T my_, T 
         for (int k = 0; k < 9; ++k)
             h[k] = (S(h[k]) / den).v;
     }
+}
+
+// ----------------------------------------------------------------------- GE
+// RHO-GE, the competitor the paper measures against (Bilaniuk et al. 2014; 221
+// flops, h33 fixed to 1 by construction, no pivoting: an axis-aligned source
+// square makes its first pivot x0 - x2 zero and the result non-finite, exactly
+// as in the reference).  Column elimination on
+//   A[2][4]: source coordinates with point 2 as origin (A[.][2] = p2 itself)
+//   B[3][8]: column j = X-equation of point j, column 4+j = its Y-equation,
+//            rows (x*T, y*T, T) relative to point 2, the first two negated.
+// Pivot order, the two reciprocals and the output permutation: MOD/GE.cpp:75-186.
+template <typename T>
+__device__ __forceinline__ void ge_combine(Strict<T> (&B)[3][8], int a, int b, Strict<T> s1,
+                                           Strict<T> s2)
+{
+#pragma unroll
+    for (int half = 0; half < 8; half += 4)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            B[r][half + a] = B[r][half + a] * s1 - B[r][half + b] * s2;
+}
+
+template <typename T>
+__device__ __forceinline__ void ge_solve(const T (&s)[8], const T (&t)[8], T (&h)[9])
+{
+    using S = Strict<T>;
+    S A[2][4], B[3][8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                 // k = 0: X-equations, 1: Y-equations
+        const S T2 = S(t[4 + k]);
+        const S xT2 = S(s[4]) * T2, yT2 = S(s[5]) * T2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j == 2) {
+                B[0][4 * k + j] = -xT2;
+                B[1][4 * k + j] = -yT2;
+                B[2][4 * k + j] = T2;
+            } else {
+                const S Tj = S(t[2 * j + k]);
+                B[0][4 * k + j] = xT2 - S(s[2 * j]) * Tj;
+                B[1][4 * k + j] = yT2 - S(s[2 * j + 1]) * Tj;
+                B[2][4 * k + j] = Tj - T2;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        A[0][j] = (j == 2) ? S(s[4]) : S(s[2 * j]) - S(s[4]);
+        A[1][j] = (j == 2) ? S(s[5]) : S(s[2 * j + 1]) - S(s[5]);
+    }
+    // x out of points 1 and 3 (pivot: point 0), then y out of points 3 and 0 (pivot: point 1)
+    S s1 = A[0][0], s2 = A[0][1];
+    A[1][1] = A[1][1] * s1 - A[1][0] * s2;
+    ge_combine<T>(B, 1, 0, s1, s2);
+    s2 = A[0][3];
+    A[1][3] = A[1][3] * s1 - A[1][0] * s2;
+    ge_combine<T>(B, 3, 0, s1, s2);
+    s1 = A[1][1];
+    s2 = A[1][3];
+    ge_combine<T>(B, 3, 1, s1, s2);
+    s2 = A[1][0];
+    A[0][0] = A[0][0] * s1;
+    ge_combine<T>(B, 0, 1, s1, s2);
+    // unit pivots
+    s1 = S(T(1)) / A[0][0];
+    s2 = S(T(1)) / A[1][1];
+#pragma unroll
+    for (int half = 0; half < 8; half += 4)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            B[r][half] = B[r][half] * s1;
+            B[r][half + 1] = B[r][half + 1] * s2;
+        }
+    // origin column
+    s1 = A[0][2];
+    s2 = A[1][2];
+#pragma unroll
+    for (int half = 0; half < 8; half += 4)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            B[r][half + 2] = B[r][half + 2] - (B[r][half] * s1 + B[r][half + 1] * s2);
+    // back-substitution of the two hollowed-out rows (columns 7, then 3)
+    s1 = B[0][7];
+    B[1][7] = B[1][7] / s1;
+    B[2][7] = B[2][7] / s1;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const S f = B[0][c];
+        B[1][c] = B[1][c] - f * B[1][7];
+        B[2][c] = B[2][c] - f * B[2][7];
+    }
+    s1 = B[1][3];
+    B[2][3] = B[2][3] / s1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (c != 3)
+            B[2][c] = B[2][c] - B[1][c] * B[2][3];
+    h[0] = B[2][0].v; h[1] = B[2][1].v; h[2] = B[2][2].v;
+    h[3] = B[2][4].v; h[4] = B[2][5].v; h[5] = B[2][6].v;
+    h[6] = B[2][7].v; h[7] = B[2][3].v; h[8] = T(1);
 }
 
 }  // namespace sksb

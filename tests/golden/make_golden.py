@@ -5,6 +5,9 @@ reference cannot travel to the GPU box).
   ref_general.npz  outputs of the reference's own C++ (MOD/ACA_SKS.cpp compiled in
                    place -> oracle/_ref/libsks_ref.so) on seeded quadruples, fp32 and
                    fp64, three input distributions + exact degenerate cases.
+  ref_ge.npz       outputs of the reference's competitor solver cv::runKernel_GE (MOD/GE.cpp,
+                   same library, fp32 only) on the image-uniform distribution, the
+                   veri_4Pts.m general quad and the degenerate cases.
   ref_torch.npz    outputs obtained by EXECUTING the reference's torch statements
                    (PY.py getInput/getTar/adjust, the body of TensorACA_rect
                    :296-302 and of ACA_vanilla :322-381) on torch-CPU.  The source
@@ -69,6 +72,23 @@ def make_ref_general():
         out[f"sks_{tag}_deg"] = r.solve("sks", s, t)
     np.savez_compressed(os.path.join(OUT, "ref_general.npz"), **out)
     print("ref_general.npz", {k: v.shape for k, v in list(out.items())[:4]}, "...")
+
+
+def make_ref_ge():
+    from oracle.oracle import Oracle, RefLib
+    o, r = Oracle(), RefLib()
+    out = {}
+    for dist in (0, 1):      # dist 0: axis-aligned source squares, GE's first pivot is zero
+        s, t = o.synth_quads(4000 * dist, 768, 21 + dist, dist, np.float32)
+        out[f"src_f32_d{dist}"], out[f"tar_f32_d{dist}"] = s, t
+        out[f"ge_f32_d{dist}"] = r.solve("ge", s, t)
+    s, t = degenerate_cases(np.float32)
+    out["src_f32_deg"], out["tar_f32_deg"], out["ge_f32_deg"] = s, t, r.solve("ge", s, t)
+    k = np.load(os.path.join(OUT, "kat_veri4pts.npz"))
+    s, t = k["src_general"][None].astype(np.float32), k["tar_general"][None].astype(np.float32)
+    out["src_f32_kat"], out["tar_f32_kat"], out["ge_f32_kat"] = s, t, r.solve("ge", s, t)
+    np.savez_compressed(os.path.join(OUT, "ref_ge.npz"), **out)
+    print("ref_ge.npz", {k: v.shape for k, v in list(out.items())[:3]}, "...")
 
 
 def _function_nodes(path):
@@ -152,3 +172,4 @@ if __name__ == "__main__":
     make_ref_general()
     make_ref_torch()
     make_kat()
+    make_ref_ge()

@@ -78,6 +78,53 @@ def test_soa_bit_exact(api, oracle, cuda, solver, dtype):
             assert_same_bits(H.cpu().numpy().T, want, f"soa {solver} n={n}")
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("variant", ["direct", "direct_16B", "ring"])
+def test_ge_competitor_bit_exact(api, sks, oracle, golden, cuda, dtype, variant):
+    """RHO-GE (MOD/GE.cpp) through the same streaming kernels:
+    AoS and SoA, ragged sizes, the reference's golden vectors, host-pointer path."""
+    set_variant(sks, variant)
+    for n, dist in (((1 << 19) + 5, 1), (4099, 0), (3, 1), (0, 1)):
+        s, t = oracle.synth_quads(17, n, 29 + dist, dist, dtype)
+        want = oracle.solve("ge", s, t).reshape(n, 9)
+        flag = torch.full((n,), 7, dtype=torch.uint8, device=cuda)
+        H = api.solve("ge", dev(s, cuda).view(n, 8), dev(t, cuda).view(n, 8), degenerate=flag)
+        assert_same_bits(H.cpu().numpy(), want, f"ge aos {dtype.__name__} n={n}")
+        assert np.array_equal(flag.cpu().numpy(), oracle.degenerate(want, True))
+        if n:
+            Hs = api.solve("ge", dev(s.T, cuda), dev(t.T, cuda), normalize=False, layout="soa")
+            assert_same_bits(Hs.cpu().numpy().T, want, f"ge soa {dtype.__name__} n={n}")
+    if dtype == np.float32:
+        g = golden["ref_ge"]
+        for case in ("d0", "d1", "deg", "kat"):
+            H = api.runKernel_GE(dev(g[f"src_f32_{case}"], cuda), dev(g[f"tar_f32_{case}"], cuda))
+            assert_same_bits(H.cpu().numpy(), g[f"ge_f32_{case}"], f"ge golden {case}")
+        s, t = oracle.synth_quads(1, 300_001, 4, 1, np.float32)
+        H = api.runKernel_GE(torch.from_numpy(s), torch.from_numpy(t))          # host pointers
+        assert_same_bits(H.numpy(), oracle.solve("ge", s, t), "ge host path")
+
+
+@pytest.mark.parametrize("solver", ["aca", "sks", "ge"])
+def test_soa_fp64_equals_reference_cuda_kernels_without_fma(api, cuda, solver):
+    """GPU-side pin of rows a5/a6 (and fp64 GE): the reference's own kernels
+    cal_Homo_ACA / cal_Homo_SKS / cal_Homo_GE (GPU.cu:81-240, :359-507) compiled with
+    -fmad=false round every operation on its own, like the reference's C++; launched as
+    the reference launches them (SoA fp64, block 32, un-normalised) they must produce
+    the same bits as our SoA kernels on the same device buffers."""
+    from oracle.oracle import RefGpuLib
+    if not RefGpuLib.available(nofma=True):
+        pytest.skip("oracle/_ref/libsks_refgpu_nofma.so not built")
+    ref = RefGpuLib(nofma=True)
+    for n, dist in (((1 << 20) + 3, 1), (100_000, 0)):
+        src, tar = api.synth_quads(n, 41, dist, torch.float64, cuda, layout="soa")
+        H_ref = torch.empty((9, n), dtype=torch.float64, device=cuda)
+        ref.run(solver, src.data_ptr(), tar.data_ptr(), H_ref.data_ptr(), n,
+                torch.cuda.current_stream().cuda_stream)
+        H = api.solve(solver, src, tar, normalize=False, layout="soa")
+        torch.cuda.synchronize()
+        assert_same_bits(H.cpu().numpy(), H_ref.cpu().numpy(), f"{solver} vs reference CUDA kernel, dist {dist}")
+
+
 @pytest.mark.parametrize("tag", ["f32", "f64"])
 @pytest.mark.parametrize("solver", ["aca", "sks"])
 def test_reference_golden_vectors(api, sks, golden, cuda, solver, tag):

@@ -27,6 +27,33 @@ def test_oracle_matches_live_reference(oracle, reflib, dtype, dist):
                          f"{solver} {dtype.__name__} dist{dist}")
 
 
+@pytest.mark.parametrize("case", ["d0", "d1", "deg", "kat"])
+def test_ge_oracle_matches_reference_golden(oracle, golden, case):
+    """Competitor solver RHO-GE against outputs of the reference's MOD/GE.cpp."""
+    g = golden["ref_ge"]
+    assert_same_bits(oracle.solve("ge", g[f"src_f32_{case}"], g[f"tar_f32_{case}"]), g[f"ge_f32_{case}"],
+                     f"ge f32 {case}")
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2])
+def test_ge_oracle_matches_live_reference(oracle, reflib, dist):
+    s, t = oracle.synth_quads(31 * dist, 200_000, 5 + dist, dist, np.float32)
+    assert_same_bits(oracle.solve("ge", s, t), reflib.solve("ge", s, t), f"ge dist{dist}")
+
+
+def test_ge_fp64_agrees_with_aca_where_it_is_defined(oracle):
+    """fp64 GE is the same type-generic elimination; on general quads it must agree with
+    ACA to the accuracy the paper reports for GE (no pivoting: ~1e-7 relative at worst),
+    and it has no answer for an axis-aligned source square (zero first pivot)."""
+    s, t = oracle.synth_quads(0, 50_000, 3, 1, np.float64)
+    ge, aca = oracle.solve("ge", s, t), oracle.solve("aca", s, t)
+    scale = np.abs(aca).max(axis=1, keepdims=True)
+    assert (np.abs(ge - aca) / scale).max() < 1e-9
+    assert reproject_error(ge, s, t).max() < 1e-6
+    sq = np.array([[10, 10, 138, 10, 10, 138, 138, 138]], dtype=np.float64)
+    assert not np.isfinite(oracle.solve("ge", sq, sq + 3.0)[0, :8]).all()
+
+
 def test_reference_threads_agree(reflib, oracle):
     s, t = oracle.synth_quads(0, 50_001, 3, 1, np.float32)
     a = reflib.solve("sks", s, t, threads=1)
