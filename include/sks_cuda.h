@@ -169,6 +169,16 @@ int sks_cuda_gather_sks_f64(const double *pool_xyXY, uint32_t pool_size, const u
                             uint64_t seed, double *H, int64_t n, int layout, int64_t ld, int flags,
                             uint8_t *degenerate, void *stream);
 
+/* The reference's sample list itself (GPU.cu:1443-1446): n 32-bit draws of cuRAND's
+ * host-API generator CURAND_RNG_PSEUDO_MRG32K3A with the given seed (the reference
+ * uses 11), offset 0, default ordering -- bit-identical to
+ *   curandCreateGenerator(&g, CURAND_RNG_PSEUDO_MRG32K3A);
+ *   curandSetPseudoRandomGeneratorSeed(g, seed);  curandGenerate(g, out, n);
+ * without linking libcurand (hand-written kernel, csrc/mrg32k3a.cuh).  With
+ * n = 4*numsOfH the buffer is the rand4 argument of the gather entry points above,
+ * which replays the reference's exact hypothesis set. */
+int sks_cuda_curand_mrg32k3a_u32(uint32_t *out, int64_t n, uint64_t seed, void *stream);
+
 /* ---- fused ACA-RANSAC ----------------------------------------------------- */
 /* New (nothing like it in the reference; sampler precedent GPU.cu:52-78).
  * corr: [n_pairs][n_pts][4] = (x,y,X,Y) fp32.  Hypothesis ids

@@ -94,6 +94,11 @@ class Oracle:
         fn(_p(src), _p(tar), C.c_int64(begin), C.c_int64(count), C.c_uint64(seed), C.c_int(dist))
         return src, tar
 
+    def curand_mrg32k3a(self, n: int, seed: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint32)
+        self.lib.oracle_curand_mrg32k3a_u32(_p(out), C.c_int64(n), C.c_uint64(seed))
+        return out
+
     def rng_u64(self, seed: int, ctr: int, lane: int) -> int:
         return int(self.lib.oracle_rng_u64(seed, ctr, lane))
 

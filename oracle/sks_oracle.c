@@ -170,6 +170,72 @@ static inline double u01_f64(uint64_t r) { return (double)(r >> 11) * 0x1p-53; }
 DEF_SYNTH(oracle_synth_quads_f32, float, u01_f32)
 DEF_SYNTH(oracle_synth_quads_f64, double, u01_f64)
 
+/* ------------------------------------------------- cuRAND MRG32K3A sample list */
+/* The reference fills its sample list with cuRAND's host API (GPU.cu:1443-1446:
+ * CURAND_RNG_PSEUDO_MRG32K3A, seed 11, curandGenerate).  cuRAND is a third-party
+ * library outside /root/reference (libcurand 10.3.10, CUDA 12.9); this restates its
+ * published algorithm -- L'Ecuyer's MRG32k3a as in CUDA's public curand_kernel.h
+ * (seeding :1276-1292, step :1061-1150, output scaling :1161-1166) -- and the host
+ * API's output order measured against the library on a B200 (tools/curand_dump.py):
+ * out[n] = draw floor(n/81920) of subsequence n mod 81920, subsequences 2^76 steps
+ * apart.  Pinned by tests/golden/curand_mrg32k3a.npz (library output, 3 seeds). */
+#define MRG_M1 4294967087ULL
+#define MRG_M2 4294944443ULL
+
+static void mrg_mat_mul(uint64_t C[9], const uint64_t A[9], const uint64_t B[9], uint64_t m)
+{
+    uint64_t r[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            uint64_t acc = 0;
+            for (int k = 0; k < 3; ++k)
+                acc = (acc + A[3 * i + k] * B[3 * k + j] % m) % m;
+            r[3 * i + j] = acc;
+        }
+    memcpy(C, r, sizeof r);
+}
+
+static void mrg_mat_vec(const uint64_t A[9], uint64_t v[3], uint64_t m)
+{
+    uint64_t r[3];
+    for (int i = 0; i < 3; ++i)
+        r[i] = ((A[3 * i] * v[0] % m + A[3 * i + 1] * v[1] % m) % m + A[3 * i + 2] * v[2] % m) % m;
+    memcpy(v, r, sizeof r);
+}
+
+void oracle_curand_mrg32k3a_u32(uint32_t *out, int64_t n, uint64_t seed)
+{
+    const int64_t T = 81920;
+    uint64_t J1[9] = { 0, 1, 0, 0, 0, 1, MRG_M1 - 810728ULL, 1403580ULL, 0 };
+    uint64_t J2[9] = { 0, 1, 0, 0, 0, 1, MRG_M2 - 1370589ULL, 0, 527612ULL };
+    for (int s = 0; s < 76; ++s) {               /* one subsequence = 2^76 steps */
+        mrg_mat_mul(J1, J1, J1, MRG_M1);
+        mrg_mat_mul(J2, J2, J2, MRG_M2);
+    }
+    uint64_t s1[3] = { 12345, 12345, 12345 }, s2[3] = { 12345, 12345, 12345 };
+    if (seed != 0) {
+        const uint64_t x1 = (uint32_t)seed ^ 0x55555555u, x2 = (uint32_t)(seed >> 32) ^ 0xAAAAAAAAu;
+        s1[0] = s1[2] = x1 * 12345 % MRG_M1;
+        s1[1] = x2 * 12345 % MRG_M1;
+        s2[0] = s2[2] = x2 * 12345 % MRG_M2;
+        s2[1] = x1 * 12345 % MRG_M2;
+    }
+    for (int64_t t = 0; t < T && t < n; ++t) {
+        uint64_t a[3] = { s1[0], s1[1], s1[2] }, b[3] = { s2[0], s2[1], s2[2] };
+        for (int64_t i = t; i < n; i += T) {
+            const uint64_t p1 = (1403580ULL * a[1] + 810728ULL * (MRG_M1 - a[0])) % MRG_M1;
+            const uint64_t p2 = (527612ULL * b[2] + 1370589ULL * (MRG_M2 - b[0])) % MRG_M2;
+            a[0] = a[1]; a[1] = a[2]; a[2] = p1;
+            b[0] = b[1]; b[1] = b[2]; b[2] = p2;
+            const uint64_t z = p1 > p2 ? p1 - p2 : p1 + MRG_M1 - p2;        /* in [1, m1] */
+            const double d = (double)z * 1.000000048662;
+            out[i] = d >= 4294967296.0 ? 0xFFFFFFFFu : (uint32_t)d;
+        }
+        mrg_mat_vec(J1, s1, MRG_M1);
+        mrg_mat_vec(J2, s2, MRG_M2);
+    }
+}
+
 /* ------------------------------------------------------------ ACA-RANSAC */
 /* Our own definition (parity unpinned, see header).
  *   sample    : 4 indices per hypothesis, idx_k = u32(seed, pair*2^32 + hyp, k)

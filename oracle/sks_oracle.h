@@ -44,6 +44,9 @@ void oracle_synth_quads_f32(float *src, float *tar, int64_t begin, int64_t count
 void oracle_synth_quads_f64(double *src, double *tar, int64_t begin, int64_t count,
                             uint64_t seed, int dist);
 
+/* cuRAND host-API MRG32K3A stream (the reference's sample list, GPU.cu:1443-1446) */
+void oracle_curand_mrg32k3a_u32(uint32_t *out, int64_t n, uint64_t seed);
+
 /* ACA-RANSAC scorer; corr is [n_pairs][n_pts][4] = (x,y,X,Y) */
 uint32_t oracle_ransac_count_f32(const float *H, const float *corr, int32_t n_pts, float thr2);
 void oracle_ransac_sample(uint64_t seed, int64_t pair, uint32_t hyp, int32_t n_pts,

@@ -251,6 +251,21 @@ def gather_solve(solver: str, pool: torch.Tensor, n: int, seed: int = 11,
     return H
 
 
+def curand_mrg32k3a(n: int, seed: int = 11, device="cuda", out: torch.Tensor | None = None) -> torch.Tensor:
+    """n uint32 draws (as int32 bits) identical to cuRAND's host-API MRG32K3A generator
+    with this seed -- the reference's sample list (GPU.cu:1443-1446) for n = 4*numsOfH;
+    reshape to [4, numsOfH] and pass as ``rand4`` to gather_samples / gather_solve."""
+    L = lib()
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=torch.device(device))
+    elif out.numel() != n or out.dtype != torch.int32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int32 tensor of n elements")
+    with torch.cuda.device(out.device):
+        L.check(L.c.sks_cuda_curand_mrg32k3a_u32(_ptr(out), n, seed, _stream_ptr(out)),
+                "sks_cuda_curand_mrg32k3a_u32")
+    return out
+
+
 # ------------------------------------------------------------------- RANSAC
 def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
                 samples: torch.Tensor | None = None, hyp_begin: int = 0,

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/sks_cuda.h"
+#include "mrg32k3a.cuh"
 #include "peer.cuh"
 #include "ransac.cuh"
 #include "stream_kernels.cuh"
@@ -316,6 +317,23 @@ SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_aca_f32, SOLVER_ACA, float)
 SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_aca_f64, SOLVER_ACA, double)
 SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_sks_f32, SOLVER_SKS, float)
 SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_sks_f64, SOLVER_SKS, double)
+
+int sks_cuda_curand_mrg32k3a_u32(uint32_t* out, int64_t n, uint64_t seed, void* stream)
+{
+    if (n < 0 || (n > 0 && out == nullptr)) return SKS_ERR_INVALID_ARG;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n == 0) return SKS_OK;
+    static const MrgJumpTable table = [] {
+        MrgJumpTable t;
+        mrg_build_jump_table(t);
+        return t;
+    }();
+    const int64_t threads = n < kMrgStreams ? n : kMrgStreams;
+    k_mrg32k3a<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        out, n, seed, table);
+    return finish_launch();
+}
 
 int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
                             const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,

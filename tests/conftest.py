@@ -33,7 +33,7 @@ def golden():
     import numpy as np
     g = os.path.join(ROOT, "tests", "golden")
     return {name: np.load(os.path.join(g, name + ".npz"))
-            for name in ("ref_general", "ref_torch", "kat_veri4pts", "ref_ge")}
+            for name in ("ref_general", "ref_torch", "kat_veri4pts", "ref_ge", "curand_mrg32k3a")}
 
 
 @pytest.fixture(scope="session")

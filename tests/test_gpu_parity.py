@@ -246,6 +246,51 @@ def test_gather_samples_matches_reference_semantics(api, cuda):
     assert torch.equal(s1, s2) and s1.shape == (n, 8)
 
 
+def test_curand_mrg32k3a_stream(api, oracle, golden, cuda):
+    """Hand-written MRG32k3a kernel == cuRAND's host-API generator (the reference's sample
+    list, GPU.cu:1443-1446): against the CPU restatement, the committed library output and,
+    when libcurand is present on the box, the live library."""
+    g = golden["curand_mrg32k3a"]
+    for n in (0, 1, 5, 81919, 81920, 81921, 4 * (1 << 20) + 3):
+        got = api.curand_mrg32k3a(n, 11, cuda).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, oracle.curand_mrg32k3a(n, 11)), n
+    for name, seed in zip(("s11", "s0", "sbig"), g["seeds"]):
+        got = api.curand_mrg32k3a(200_000, int(seed), cuda).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got[:4096], g[f"{name}_head"])
+        assert np.array_equal(got[81920 - 16:81920 + 4096], g[f"{name}_wrap"])
+    try:
+        lib = C.CDLL("libcurand.so.10")
+    except OSError:
+        return
+    n = 1_000_003
+    gen = C.c_void_p()
+    assert lib.curandCreateGenerator(C.byref(gen), 121) == 0           # CURAND_RNG_PSEUDO_MRG32K3A
+    assert lib.curandSetPseudoRandomGeneratorSeed(gen, C.c_ulonglong(11)) == 0
+    buf = torch.empty(n, dtype=torch.int32, device=cuda)
+    assert lib.curandGenerate(gen, C.c_void_p(buf.data_ptr()), C.c_size_t(n)) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(buf, api.curand_mrg32k3a(n, 11, cuda)), "differs from live libcurand"
+    lib.curandDestroyGenerator(gen)
+
+
+def test_reference_gpu_flow_replayed(api, oracle, cuda):
+    """The reference's whole GPU flow (GPU.cu:1443-1464) on its own fixture: cuRAND
+    MRG32K3A(seed 11) sample list -> get_rand_list -> cal_Homo_ACA, here as list kernel +
+    fused gather-solve, against the CPU restatement of each step (synthetic 2540-match pool:
+    the fixture file itself does not travel to the GPU box)."""
+    rng = np.random.default_rng(4)           # a 2540-match pool like the reference's fixture
+    pool = (rng.random((2540, 4)) * 700 + 20).astype(np.float64)
+    n = 100_000
+    r = oracle.curand_mrg32k3a(4 * n, 11).reshape(4, n)
+    idx = (r % pool.shape[0]).T                                # [n,4], as GPU.cu:55-58
+    s = pool[idx][:, :, :2].reshape(n, 8)
+    t = pool[idx][:, :, 2:].reshape(n, 8)
+    want = oracle.solve("aca", s, t, normalize=False)
+    rand4 = api.curand_mrg32k3a(4 * n, 11, cuda).view(4, n)
+    H = api.gather_solve("aca", dev(pool, cuda), n, rand4=rand4, normalize=False, layout="soa")
+    assert_same_bits(H.cpu().numpy().T, want, "replayed reference flow")
+
+
 def test_fp64_accuracy_tier(api, oracle, cuda):
     """BASELINE config 4 tier on the GPU results: SKS64 == ACA64 to ~1e-12 and
     reprojection far below 1e-4 px."""

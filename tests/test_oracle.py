@@ -161,6 +161,20 @@ def test_cv2_cross_check(oracle):
     assert reproject_error(k, s, t).max() < 1e-6
 
 
+def test_curand_mrg32k3a_restatement_matches_library_output(oracle, golden):
+    """The reference's sample list (GPU.cu:1443-1446) comes from cuRAND's host-API MRG32K3A
+    generator; the golden slices are libcurand 10.3 output on a B200 (tools/curand_dump.py),
+    including the 81920-subsequence wrap-around of its output order."""
+    g, T = golden["curand_mrg32k3a"], 81920
+    for name, seed in zip(("s11", "s0", "sbig"), g["seeds"]):
+        a = oracle.curand_mrg32k3a(2 * T + 1024, int(seed))
+        assert np.array_equal(a[:4096], g[f"{name}_head"])
+        assert np.array_equal(a[T - 16:T + 4096], g[f"{name}_wrap"])
+        assert np.array_equal(a[2 * T - 16:2 * T + 1024], g[f"{name}_wrap2"])
+    assert np.array_equal(oracle.curand_mrg32k3a(5, 11), g["s11_head"][:5])       # n < 81920
+    assert oracle.curand_mrg32k3a(0, 11).size == 0
+
+
 def test_synth_is_counter_based(oracle):
     a_s, a_t = oracle.synth_quads(100, 50, 11, 1, np.float32)
     b_s, b_t = oracle.synth_quads(0, 200, 11, 1, np.float32)

@@ -66,7 +66,10 @@ for n in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
 import numpy as np
 n = 1 << 24
 pool = torch.from_numpy(np.random.default_rng(0).uniform(7, 790, size=(2540, 4))).to(dev)
-rand4 = torch.randint(0, 2**31, (4, n), dtype=torch.int64, device=dev).to(torch.int32)
+# the reference's own sample list: cuRAND host-API MRG32K3A, seed 11 (GPU.cu:1443-1446), from our kernel
+t_list = time_us(lambda: api.curand_mrg32k3a(4 * n, 11, dev), 20)
+rand4 = api.curand_mrg32k3a(4 * n, 11, dev).view(4, n)
+print(f"sample list: 4 x 2^24 MRG32K3A draws (cuRAND host-API order) {t_list:9.1f} us")
 H = torch.empty((9, n), dtype=torch.float64, device=dev)
 for solver in ("aca", "sks"):
     def two_kernels():
