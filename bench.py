@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--ref-log2n", type=int, default=24)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="multi-rank runs: do not pin the rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 3)          # timing rules: W >= 3
@@ -226,7 +228,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from sks_homography_b200 import api, lib
+    from sks_homography_b200 import dist as sdist
     L = lib()
+    # one process per GPU: keep the rank's host threads and pinned buffers on its GPU's socket
+    args.numa = sdist.bind_to_gpu_numa_node(local) if (world > 1 and not args.no_numa_bind) else {"bound": False}
     L.check(L.c.sks_cuda_set_variant(args.variant), "set_variant")
     L.check(L.c.sks_cuda_set_tuning(args.small_tile, args.stages, args.ctas), "set_tuning")
 
@@ -329,7 +334,8 @@ def main():
         e2e = {"value": world * ne * args.e2e_steps / el, "unit": UNIT,
                "h2d_bytes_per_step": ne * in_elems * esz, "d2h_bytes_per_step": ne * 9 * esz,
                "steps": args.e2e_steps, "quadruples_per_step_per_gpu": ne,
-               "api": "sks_host_* (pinned host buffers, chunked H2D/kernel/D2H ring)"}
+               "api": "sks_host_* (pinned host buffers, chunked H2D/kernel/D2H ring)",
+               "numa_binding": args.numa}
         # the host path must give the same bytes as the device path
         if not torch.equal(hH.view(torch.int32 if dt == "f32" else torch.int64),
                            H[:ne].cpu().view(torch.int32 if dt == "f32" else torch.int64)):

@@ -202,6 +202,19 @@ int sks_cuda_ransac_finalize_f32(const float *corr, int64_t n_pairs, int32_t n_p
                                  float thr2, const unsigned long long *best_key, float *H_best,
                                  uint32_t *inlier_count, uint8_t *inlier_mask, void *stream);
 
+/* ---- consumer after the path: sampling grids for image warping ------------- */
+/* New (the reference only remarks that warping does not need the normalisation,
+ * ML/ACA_rect.m:33-35).  grid_xy[n][gh][gw][2] = (u, v) * (1/w) with (u,v,w) =
+ * H * (x0 + i*dx, y0 + j*dy, 1); H[n][9] may be at any scale.  The fused form runs
+ * ACA-rect on tar[n][8] (arguments as sks_cuda_aca_rect_f32) up to scale in
+ * registers and never writes H.  HBM-bound on the 8-byte-per-point output. */
+int sks_cuda_warp_grid_f32(const float *H, int64_t n, float x0, float y0, float dx, float dy,
+                           int32_t gw, int32_t gh, float *grid_xy, void *stream);
+int sks_cuda_aca_rect_warp_grid_f32(const float *tar, const float *M, float mx, float my,
+                                    float width, float ratio, int64_t n, float x0, float y0,
+                                    float dx, float dy, int32_t gw, int32_t gh, float *grid_xy,
+                                    void *stream);
+
 /* ---- synthetic inputs (bench / tests), generated on the device ------------ */
 /* Counter-based generator, bit-identical to oracle_synth_quads_* for the same
  * (seed, dist); distributions per SURVEY.md 8(d) (PY.py:9-21, ML/veri_4Pts.m). */

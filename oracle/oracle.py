@@ -94,6 +94,13 @@ class Oracle:
         fn(_p(src), _p(tar), C.c_int64(begin), C.c_int64(count), C.c_uint64(seed), C.c_int(dist))
         return src, tar
 
+    def warp_grid(self, H, gw: int, gh: int, x0=0.0, y0=0.0, dx=1.0, dy=1.0) -> np.ndarray:
+        H = _c(H, np.float32).reshape(-1, 9)
+        out = np.empty((H.shape[0], gh, gw, 2), dtype=np.float32)
+        self.lib.oracle_warp_grid_f32(_p(H), C.c_int64(H.shape[0]), C.c_float(x0), C.c_float(y0),
+                                      C.c_float(dx), C.c_float(dy), C.c_int32(gw), C.c_int32(gh), _p(out))
+        return out
+
     def curand_mrg32k3a(self, n: int, seed: int) -> np.ndarray:
         out = np.empty(n, dtype=np.uint32)
         self.lib.oracle_curand_mrg32k3a_u32(_p(out), C.c_int64(n), C.c_uint64(seed))

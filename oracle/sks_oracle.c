@@ -170,6 +170,28 @@ static inline double u01_f64(uint64_t r) { return (double)(r >> 11) * 0x1p-53; }
 DEF_SYNTH(oracle_synth_quads_f32, float, u01_f32)
 DEF_SYNTH(oracle_synth_quads_f64, double, u01_f64)
 
+/* ------------------------------------------------------------ warp grid */
+/* Our own definition (parity unpinned: the reference only remarks that warping
+ * needs no normalisation, ML/ACA_rect.m:33-35); mirrors csrc/warp.cuh. */
+void oracle_warp_grid_f32(const float *H, int64_t n, float x0, float y0, float dx, float dy,
+                          int32_t gw, int32_t gh, float *out)
+{
+    for (int64_t s = 0; s < n; ++s) {
+        const float *h = H + 9 * s;
+        for (int32_t j = 0; j < gh; ++j)
+            for (int32_t i = 0; i < gw; ++i) {
+                const float x = fmaf((float)i, dx, x0), y = fmaf((float)j, dy, y0);
+                const float u = fmaf(h[0], x, fmaf(h[1], y, h[2]));
+                const float v = fmaf(h[3], x, fmaf(h[4], y, h[5]));
+                const float w = fmaf(h[6], x, fmaf(h[7], y, h[8]));
+                float *o = out + 2 * (((int64_t)s * gh + j) * gw + i);
+                const float r = 1.0f / w;
+                o[0] = u * r;
+                o[1] = v * r;
+            }
+    }
+}
+
 /* ------------------------------------------------- cuRAND MRG32K3A sample list */
 /* The reference fills its sample list with cuRAND's host API (GPU.cu:1443-1446:
  * CURAND_RNG_PSEUDO_MRG32K3A, seed 11, curandGenerate).  cuRAND is a third-party

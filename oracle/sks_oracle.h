@@ -44,6 +44,10 @@ void oracle_synth_quads_f32(float *src, float *tar, int64_t begin, int64_t count
 void oracle_synth_quads_f64(double *src, double *tar, int64_t begin, int64_t count,
                             uint64_t seed, int dist);
 
+/* sampling grid of a homography (consumer after the path; our definition) */
+void oracle_warp_grid_f32(const float *H, int64_t n, float x0, float y0, float dx, float dy,
+                          int32_t gw, int32_t gh, float *out);
+
 /* cuRAND host-API MRG32K3A stream (the reference's sample list, GPU.cu:1443-1446) */
 void oracle_curand_mrg32k3a_u32(uint32_t *out, int64_t n, uint64_t seed);
 

@@ -251,6 +251,41 @@ def gather_solve(solver: str, pool: torch.Tensor, n: int, seed: int = 11,
     return H
 
 
+def warp_grid(H: torch.Tensor, gw: int, gh: int, x0: float = 0.0, y0: float = 0.0, dx: float = 1.0,
+              dy: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Sampling grid [n, gh, gw, 2] = H * (x0 + i*dx, y0 + j*dy, 1), dehomogenised; H [n,9] or
+    [n,3,3] fp32 at any scale (the step after the solver in a deep-homography pipeline)."""
+    L = lib()
+    H = H.contiguous()
+    n = H.numel() // 9
+    if out is None:
+        out = torch.empty((n, gh, gw, 2), dtype=torch.float32, device=H.device)
+    with torch.cuda.device(H.device):
+        L.check(L.c.sks_cuda_warp_grid_f32(_ptr(H), n, x0, y0, dx, dy, gw, gh, _ptr(out), _stream_ptr(H)),
+                "sks_cuda_warp_grid_f32")
+    return out
+
+
+def aca_rect_warp_grid(tar: torch.Tensor, width: float, ratio: float, gw: int, gh: int,
+                       M_x: float = 0.0, M_y: float = 0.0, M: torch.Tensor | None = None,
+                       x0: float = 0.0, y0: float = 0.0, dx: float = 1.0, dy: float = 1.0,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    """ACA-rect on tar [n,8] fused with warp_grid: the homography stays in registers (no
+    normalisation, ML/ACA_rect.m:33-35) and only the grid [n, gh, gw, 2] is written."""
+    L = lib()
+    tar = tar.contiguous()
+    n = tar.numel() // 8
+    if M is not None:
+        M = M.contiguous()
+    if out is None:
+        out = torch.empty((n, gh, gw, 2), dtype=torch.float32, device=tar.device)
+    with torch.cuda.device(tar.device):
+        L.check(L.c.sks_cuda_aca_rect_warp_grid_f32(_ptr(tar), _ptr(M), M_x, M_y, width, ratio, n, x0, y0,
+                                                    dx, dy, gw, gh, _ptr(out), _stream_ptr(tar)),
+                "sks_cuda_aca_rect_warp_grid_f32")
+    return out
+
+
 def curand_mrg32k3a(n: int, seed: int = 11, device="cuda", out: torch.Tensor | None = None) -> torch.Tensor:
     """n uint32 draws (as int32 bits) identical to cuRAND's host-API MRG32K3A generator
     with this seed -- the reference's sample list (GPU.cu:1443-1446) for n = 4*numsOfH;

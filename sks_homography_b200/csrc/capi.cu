@@ -15,6 +15,7 @@
 #include "ransac.cuh"
 #include "stream_kernels.cuh"
 #include "synth.cuh"
+#include "warp.cuh"
 
 using namespace sksb;
 
@@ -317,6 +318,59 @@ SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_aca_f32, SOLVER_ACA, float)
 SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_aca_f64, SOLVER_ACA, double)
 SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_sks_f32, SOLVER_SKS, float)
 SKS_DEFINE_GATHER_SOLVE(sks_cuda_gather_sks_f64, SOLVER_SKS, double)
+
+namespace {
+int launch_warp_grid(const float* H, const float* tar, const float* M, RectParams<float> rp,
+                     int64_t n, float x0, float y0, float dx, float dy, int32_t gw, int32_t gh,
+                     float* out, void* stream)
+{
+    if (n < 0 || gw <= 0 || gh <= 0 || out == nullptr || (H == nullptr && tar == nullptr))
+        return SKS_ERR_INVALID_ARG;
+    if (!aligned16(out) || (tar != nullptr && !aligned16(tar))) return SKS_ERR_UNALIGNED;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n == 0) return SKS_OK;
+    const GridSpec g{x0, y0, dx, dy, gw, gh};
+    const int64_t m = (int64_t)gw * gh;
+    if (m >= (int64_t)1 << 31) return SKS_ERR_INVALID_ARG;
+    // about 8-16 points per thread: group = largest power of two <= m/8 (1..256); beyond
+    // 256 x 16 points, several CTAs per sample
+    WarpSplit ws{1, 1, 0, 0};
+    while (ws.group < 256 && (int64_t)ws.group * 16 <= m) ws.group *= 2;
+    if (ws.group == 256) ws.parts = (int32_t)((m + 4095) / 4096);
+    const uint32_t stride = 2u * (uint32_t)ws.group * (uint32_t)ws.parts;
+    ws.step_i = stride % (uint32_t)gw;
+    ws.step_j = stride / (uint32_t)gw;
+    const int64_t per_cta = 256 / ws.group;
+    const int64_t ctas = ((n + per_cta - 1) / per_cta) * ws.parts;
+    if (ctas >= (int64_t)1 << 31) return SKS_ERR_INVALID_ARG;
+    if (H != nullptr)
+        k_warp_grid<false><<<(unsigned)ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            H, nullptr, nullptr, rp, g, ws, out, n);
+    else
+        k_warp_grid<true><<<(unsigned)ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            nullptr, tar, M, rp, g, ws, out, n);
+    if (int rc = finish_launch()) return rc;
+    return SKS_OK;
+}
+}  // namespace
+
+int sks_cuda_warp_grid_f32(const float* H, int64_t n, float x0, float y0, float dx, float dy,
+                           int32_t gw, int32_t gh, float* grid_xy, void* stream)
+{
+    if (H == nullptr) return SKS_ERR_INVALID_ARG;
+    return launch_warp_grid(H, nullptr, nullptr, RectParams<float>{}, n, x0, y0, dx, dy, gw, gh, grid_xy,
+                            stream);
+}
+
+int sks_cuda_aca_rect_warp_grid_f32(const float* tar, const float* M, float mx, float my, float width,
+                                    float ratio, int64_t n, float x0, float y0, float dx, float dy,
+                                    int32_t gw, int32_t gh, float* grid_xy, void* stream)
+{
+    if (tar == nullptr) return SKS_ERR_INVALID_ARG;
+    return launch_warp_grid(nullptr, tar, M, RectParams<float>{mx, my, width, ratio}, n, x0, y0, dx, dy,
+                            gw, gh, grid_xy, stream);
+}
 
 int sks_cuda_curand_mrg32k3a_u32(uint32_t* out, int64_t n, uint64_t seed, void* stream)
 {

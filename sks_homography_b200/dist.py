@@ -29,6 +29,40 @@ def shard_range(n: int, rank: int | None = None, world_size: int | None = None, 
     return lib().shard_range(n, rank, world_size)
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process's host threads to the CPUs of the NUMA node its GPU hangs off, so that
+    the pinned host buffers it allocates afterwards (first touch) and the staging memcpys of
+    the host-pointer path stay on the socket that owns the PCIe link.  One process per GPU on
+    a two-socket box otherwise puts about half of the ranks' buffers across the socket
+    interconnect.  Pure sysfs + sched_setaffinity; a no-op (with the reason reported) where
+    the topology is not visible."""
+    import os
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read())
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+        info.update(pci=bdf, numa_node=node, local_cpulist=cpulist)
+        cpus = set()
+        for part in cpulist.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if node < 0 or not cpus or cpus == allowed:
+            info["reason"] = "single node or topology not exposed"
+            return info
+        os.sched_setaffinity(0, cpus)
+        info.update(bound=True, cpus=len(cpus))
+    except Exception as e:                                    # sysfs absent, container limits...
+        info["reason"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 def merge_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     """In-place max-combine of packed (count<<32 | ~hyp) keys across ranks.
 

@@ -246,6 +246,27 @@ def test_gather_samples_matches_reference_semantics(api, cuda):
     assert torch.equal(s1, s2) and s1.shape == (n, 8)
 
 
+@pytest.mark.parametrize("gw,gh", [(32, 32), (33, 5), (1, 1), (128, 128)])
+def test_warp_grid_consumer(api, oracle, cuda, gw, gh):
+    """Sampling grid after the solver: from stored H and fused with
+    ACA-rect (H never written); bit-exact against the CPU port, even and odd grid sizes."""
+    n = 257
+    _, t = oracle.synth_quads(3, n, 5, 0, np.float32)
+    H = oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0, normalize=False)
+    spec = dict(x0=15.0, y0=12.0, dx=128.0 / max(gw - 1, 1), dy=128.0 / max(gh - 1, 1))
+    want = oracle.warp_grid(H, gw, gh, **spec)
+    got = api.warp_grid(dev(H, cuda), gw, gh, **spec)
+    assert_same_bits(got.cpu().numpy(), want, "warp_grid from H")
+    guard = torch.full((n * gh * gw * 2 + 64,), 7.0, dtype=torch.float32, device=cuda)
+    fused = api.aca_rect_warp_grid(dev(t, cuda), 128.0, 1.0, gw, gh, M_x=15.0, M_y=12.0,
+                                   out=guard[: n * gh * gw * 2].view(n, gh, gw, 2), **spec)
+    assert_same_bits(fused.cpu().numpy(), want, "fused ACA-rect + warp_grid")
+    assert (guard[n * gh * gw * 2:] == 7.0).all()
+    if gw > 1 and gh > 1:          # the grid's corners are the rectangle's corners: they land on tar
+        c = fused.cpu().numpy()[:, [0, 0, -1, -1], [0, -1, 0, -1], :].reshape(n, 8)
+        assert np.abs(c - t).max() < 2e-3
+
+
 def test_curand_mrg32k3a_stream(api, oracle, golden, cuda):
     """Hand-written MRG32k3a kernel == cuRAND's host-API generator (the reference's sample
     list, GPU.cu:1443-1446): against the CPU restatement, the committed library output and,

@@ -175,6 +175,15 @@ def test_curand_mrg32k3a_restatement_matches_library_output(oracle, golden):
     assert oracle.curand_mrg32k3a(0, 11).size == 0
 
 
+def test_warp_grid_port_maps_rectangle_corners_to_targets(oracle):
+    _, t = oracle.synth_quads(0, 64, 9, 0, np.float32)
+    H = oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0, normalize=False)
+    g = oracle.warp_grid(H, 2, 2, x0=15.0, y0=12.0, dx=128.0, dy=128.0)
+    assert np.abs(g.reshape(64, 8) - t).max() < 2e-3          # TL,TR,BL,BR order, fp32 solve
+    Hn = oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0, normalize=True)
+    assert np.abs(oracle.warp_grid(Hn, 2, 2, 15.0, 12.0, 128.0, 128.0) - g).max() < 2e-3   # scale-free
+
+
 def test_synth_is_counter_based(oracle):
     a_s, a_t = oracle.synth_quads(100, 50, 11, 1, np.float32)
     b_s, b_t = oracle.synth_quads(0, 200, 11, 1, np.float32)
