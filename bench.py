@@ -38,6 +38,29 @@ sys.path.insert(0, ROOT)
 METRIC = "ACA/SKS homographies/s"
 UNIT = "homographies/s"
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner,
+# torchrun notices), so stdout's file descriptor is pointed at stderr for the whole run and the
+# line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 WORKLOADS = {
     # name: (solver, dtype, bytes per homography (algorithmic), default log2 n, dist)
     "aca_f32": ("aca", "f32", 100, 26, 0),     # BASELINE configs[1]  (headline)
@@ -124,11 +147,11 @@ def run_reference(args):
     import numpy as np
     from oracle.oracle import Oracle, RefLib
     if args.workload == "ransac":
-        print(json.dumps({"impl": "reference", "unavailable": "the reference has no RANSAC scorer"}))
+        emit({"impl": "reference", "unavailable": "the reference has no RANSAC scorer"})
         return 0
     solver, dt, bytes_per_h, log2n, dist = WORKLOADS[args.workload]
     if solver == "rect":
-        print(json.dumps({"impl": "reference", "unavailable": "the reference has no C++ ACA-rect"}))
+        emit({"impl": "reference", "unavailable": "the reference has no C++ ACA-rect"})
         return 0
     o = Oracle()
     kind = "reference"
@@ -166,7 +189,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -207,6 +230,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="multi-rank runs: do not pin the rank to its GPU's NUMA node")
     args = ap.parse_args()
+    _capture_stdout()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 3)          # timing rules: W >= 3
     if args.impl == "reference":
@@ -398,7 +422,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "gpu_baseline": gpu_base,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -608,7 +632,7 @@ def run_ransac(args, api, L, dev, rank, world, local):
             "mean_inlier_fraction_of_winner": float(cnt.mean().item()) / n_pts,
             "peer_reduce_timed_out": reducer.timed_out() if reducer else None,
         }
-        print(json.dumps(line))
+        emit(line)
     if reducer is not None:
         reducer.close()
     if world > 1:
