@@ -396,7 +396,21 @@ def main():
             v = np.uint32 if dt == "f32" else np.uint64
             ok = (got.view(v) == out.view(v)) | (np.isnan(got) & np.isnan(out))
             parity = {"checked_quadruples": int(S), "mismatching_elements": int((~ok).sum())}
-        cpu = {"value": S / best, "unit": UNIT, "cores": threads, "kind": kind,
+        o3 = None
+        if kind == "reference":
+            try:                       # speed-only: the same files at -O3 with AVX2/FMA (bits differ)
+                ref3 = RefLib(o3=True)
+                out3 = np.empty_like(out)
+                ref3.solve(solver, s_h, t_h, threads=threads, out=out3)
+                b3 = 1e30
+                for _ in range(5):
+                    t0 = time.perf_counter(); ref3.solve(solver, s_h, t_h, threads=threads, out=out3)
+                    b3 = min(b3, time.perf_counter() - t0)
+                o3 = {"value": S / b3, "flags": "g++ -O3 -march=x86-64-v3 -ffp-contract=fast",
+                      "max_rel_diff_vs_O2": float(np.nanmax(np.abs(out3 - out) / np.maximum(np.abs(out), 1e-30)))}
+            except Exception as e:
+                o3 = {"unavailable": str(e)[:100]}
+        cpu = {"value": S / best, "unit": UNIT, "cores": threads, "kind": kind, "o3_fma_build": o3,
                "sample": f"first 2^{args.cpu_log2n} quadruples of the workload, best of 5 passes, "
                          f"{'MOD/GE.cpp' if solver == 'ge' else 'MOD/ACA_SKS.cpp'} g++ -O2 -ffp-contract=off"
                          f"{'' if kind == 'reference' else ' (oracle port)'}, {threads} threads",

@@ -19,6 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libsks_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsks_ref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "libsks_ref_o3.so")
 REFGPU_SO = os.path.join(HERE, "_ref", "libsks_refgpu.so")
 REFGPU_NOFMA_SO = os.path.join(HERE, "_ref", "libsks_refgpu_nofma.so")
 REFERENCE_ROOT = "/root/reference"
@@ -27,7 +28,7 @@ REFERENCE_ROOT = "/root/reference"
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference checkout exists)."""
     need = force or not os.path.exists(ORACLE_SO)
-    if os.path.isdir(REFERENCE_ROOT) and not all(os.path.exists(f) for f in (REF_SO, REFGPU_SO, REFGPU_NOFMA_SO)):
+    if os.path.isdir(REFERENCE_ROOT) and not all(os.path.exists(f) for f in (REF_SO, REF_O3_SO, REFGPU_SO, REFGPU_NOFMA_SO)):
         need = True
     if need:
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True,
@@ -151,13 +152,16 @@ class Oracle:
 class RefLib:
     """The reference's own C++ (bit-exact ground truth for SKS / ACA)."""
 
-    def __init__(self):
+    def __init__(self, o3: bool = False):
+        """o3=True: the -O3 -march=x86-64-v3 -ffp-contract=fast build (speed comparator only:
+        FMA contraction changes bits)."""
         build()
-        if not os.path.exists(REF_SO):
+        so = REF_O3_SO if o3 else REF_SO
+        if not os.path.exists(so):
             raise FileNotFoundError(
-                f"{REF_SO} missing: it is built from /root/reference by `make -C oracle ref` in "
+                f"{so} missing: it is built from /root/reference by `make -C oracle ref` in "
                 "the authoring container and travels to the GPU box as a prebuilt file")
-        self.lib = C.CDLL(REF_SO)
+        self.lib = C.CDLL(so)
         self.lib.ref_hardware_threads.restype = C.c_int
 
     @staticmethod

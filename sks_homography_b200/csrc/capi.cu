@@ -168,7 +168,9 @@ int launch_gather_solve(const T* pool, uint32_t pool_size, const uint32_t* rand4
     if (ld < n) return SKS_ERR_INVALID_ARG;
     constexpr int TILE = sizeof(T) == 4 ? 256 : 128;
     const int64_t grid = (n + TILE - 1) / TILE;
-    k_gather_solve<SOLVER, T, TILE><<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(
+    const bool wide = sizeof(T) == 8 && aligned32(pool) && g_wide.load() != 0;
+    auto kern = wide ? k_gather_solve<SOLVER, T, TILE, true> : k_gather_solve<SOLVER, T, TILE, false>;
+    kern<<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(
         pool, pool_size, rand4, seed_key(seed), H, degen, n, layout, ld,
         (flags & SKS_FLAG_NORMALIZE) != 0);
     return finish_launch();

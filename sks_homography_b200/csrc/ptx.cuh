@@ -99,6 +99,17 @@ __device__ __forceinline__ Chunk32 ldg_stream32(const void* p)
         : "l"(p));
     return c;
 }
+// 256-bit load through the read-only path that DOES allocate in L1: one whole 32-byte sector
+// per lane, for gathers from a small table that should stay resident (fp64 match pool)
+__device__ __forceinline__ Chunk32 ldg_nc32(const void* p)
+{
+    Chunk32 c;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]),
+                   "=r"(c.w[6]), "=r"(c.w[7])
+                 : "l"(p));
+    return c;
+}
 __device__ __forceinline__ void stg_stream32(void* p, const Chunk32& c)
 {
     asm volatile(

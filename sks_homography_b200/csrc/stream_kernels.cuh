@@ -292,7 +292,10 @@ k_rect_planar34(const T* __restrict__ tar34, const T* __restrict__ src34, RectPa
 // here: each thread draws its four pool indices (r % pool_size, repeats allowed,
 // GPU.cu:55-58; from the caller's [4][n] list or the counter RNG), gathers the
 // matches from the L1/L2-resident pool, solves, and only H leaves the SM.
-template <int SOLVER, typename T, int TILE>
+// WIDE (fp64, 32-byte aligned pool): a match (x,y,X,Y) is exactly one 32-byte sector and arrives
+// with ONE 256-bit load instead of two 16-byte ones -- the kernel is bound by L1 gather
+// wavefronts (32 random sectors per warp instruction), so this halves its dominant cost.
+template <int SOLVER, typename T, int TILE, bool WIDE>
 __global__ void __launch_bounds__(TILE)
 k_gather_solve(const T* __restrict__ pool, uint32_t pool_size, const uint32_t* __restrict__ rand4,
                uint64_t key, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, int layout,
@@ -320,6 +323,12 @@ k_gather_solve(const T* __restrict__ pool, uint32_t pool_size, const uint32_t* _
             if constexpr (sizeof(T) == 4) {
                 const float4 m = __ldg(reinterpret_cast<const float4*>(c));
                 s[2 * k] = m.x; s[2 * k + 1] = m.y; t[2 * k] = m.z; t[2 * k + 1] = m.w;
+            } else if constexpr (WIDE) {
+                const Chunk32 m = ldg_nc32(c);
+                s[2 * k] = __hiloint2double((int)m.w[1], (int)m.w[0]);
+                s[2 * k + 1] = __hiloint2double((int)m.w[3], (int)m.w[2]);
+                t[2 * k] = __hiloint2double((int)m.w[5], (int)m.w[4]);
+                t[2 * k + 1] = __hiloint2double((int)m.w[7], (int)m.w[6]);
             } else {
                 const double2 a = __ldg(reinterpret_cast<const double2*>(c));
                 const double2 b = __ldg(reinterpret_cast<const double2*>(c) + 1);
