@@ -6,6 +6,9 @@ sks_homography_b200.api; there is still no CPU compute path.
     torch.ops.sks_b200.solve(src, tar, "aca" | "sks", normalize)      -> H [n, 9]
     torch.ops.sks_b200.aca_rect(tar, M, mx, my, width, ratio, normalize) -> H [n, 9]
     torch.ops.sks_b200.ransac(corr, n_hyp, seed, thr2)                -> (H [P,9], count [P], hyp [P])
+    torch.ops.sks_b200.rect_warp_grid(tar, M, mx, my, width, ratio, gw, gh, x0, y0, dx, dy)
+                                                                      -> grid [n, gh, gw, 2]
+"solve" also takes "ge" (the competitor RHO-GE).
 """
 from __future__ import annotations
 
@@ -49,3 +52,15 @@ def _(corr, n_hyp, seed, thr2):
     P = corr.shape[0]
     return (corr.new_empty((P, 9)), corr.new_empty((P,), dtype=torch.int32),
             corr.new_empty((P,), dtype=torch.int64))
+
+
+@torch.library.custom_op("sks_b200::rect_warp_grid", mutates_args=())
+def rect_warp_grid(tar: Tensor, M: Tensor | None, mx: float, my: float, width: float, ratio: float,
+                   gw: int, gh: int, x0: float, y0: float, dx: float, dy: float) -> Tensor:
+    return api.aca_rect_warp_grid(tar.reshape(-1, 8), width, ratio, gw, gh, M_x=mx, M_y=my, M=M,
+                                  x0=x0, y0=y0, dx=dx, dy=dy)
+
+
+@rect_warp_grid.register_fake
+def _(tar, M, mx, my, width, ratio, gw, gh, x0, y0, dx, dy):
+    return tar.new_empty((tar.numel() // 8, gh, gw, 2))

@@ -20,6 +20,9 @@ def test_ops_are_registered_and_trace_with_fake_tensors(sks):
         assert R.shape == (7, 9) and R.dtype == torch.float64
         Hb, cnt, hyp = torch.ops.sks_b200.ransac(torch.empty(5, 64, 4), 128, 1, 4.0)
         assert Hb.shape == (5, 9) and cnt.shape == (5,) and hyp.dtype == torch.int64
+        G = torch.ops.sks_b200.rect_warp_grid(torch.empty(6, 8), None, 0.0, 0.0, 128.0, 1.0, 16, 12,
+                                              0.0, 0.0, 1.0, 1.0)
+        assert G.shape == (6, 12, 16, 2)
 
 
 @pytest.mark.gpu
@@ -30,6 +33,12 @@ def test_ops_match_oracle_on_gpu(sks, oracle, cuda):
     assert_same_bits(H.cpu().numpy(), oracle.solve("sks", s, t), "torch op sks")
     R = torch.ops.sks_b200.aca_rect(torch.from_numpy(t).to(cuda), None, 15.0, 12.0, 128.0, 1.0, True)
     assert_same_bits(R.cpu().numpy(), oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0), "torch op rect")
+    G = torch.ops.sks_b200.solve(torch.from_numpy(s).to(cuda), torch.from_numpy(t).to(cuda), "ge", True)
+    assert_same_bits(G.cpu().numpy(), oracle.solve("ge", s, t), "torch op ge")
+    W = torch.ops.sks_b200.rect_warp_grid(torch.from_numpy(t).to(cuda), None, 15.0, 12.0, 128.0, 1.0, 9, 7,
+                                          15.0, 12.0, 16.0, 21.0)
+    Hu = oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0, normalize=False)
+    assert_same_bits(W.cpu().numpy(), oracle.warp_grid(Hu, 9, 7, 15.0, 12.0, 16.0, 21.0), "torch op warp grid")
     torch.library.opcheck(torch.ops.sks_b200.solve.default,
                           (torch.from_numpy(s[:64]).to(cuda), torch.from_numpy(t[:64]).to(cuda), "aca", False),
                           test_utils=("test_schema", "test_faketensor"))
