@@ -88,3 +88,40 @@ def test_config4_sks_f64_2pow25(api, sks, oracle, cuda):
     q = torch.einsum("nij,nkj->nki", Hm, p)
     err = ((q[..., :2] / q[..., 2:3]) - tar.view(n, 4, 2)).norm(dim=2).amax(1)
     assert float(err.max()) < 1e-6
+
+
+def test_config5_ransac_1024x4096x65536(api, sks, oracle, cuda):
+    """BASELINE configs[4] at full size (6.9e10 hypothesis x match evaluations): the CPU oracle
+    cannot repeat it, so check what does not depend on size -- 8 hypothesis shards merged by max
+    == one launch; the finalize kernel's recount and inlier mask == the winning key; for a few
+    pairs the winner rebuilt by the oracle has exactly that count and no hypothesis of an
+    oracle-scored id window beats it; every scorer variant returns the same keys."""
+    P, n_pts, n_hyp, seed, thr2 = 1024, 4096, 65536, 11, 2.25
+    corr = api.synth_corr(P, n_pts, seed=seed, inlier_permille=500, noise=0.5, device=cuda)
+    full = api.ransac_keys(corr, n_hyp, seed, thr2)
+    merged = torch.zeros(P, dtype=torch.int64, device=cuda)
+    for r in range(8):
+        b, c = sks.shard_range(n_hyp, r, 8)
+        api.ransac_keys(corr, n_hyp, seed, thr2, None, b, c, out=merged)
+    assert torch.equal(merged, full)
+    H, cnt, mask = api.ransac_finalize(corr, n_hyp, seed, thr2, full, want_mask=True)
+    kc, hyp = api.decode_keys(full)
+    assert torch.equal(cnt.long(), kc) and torch.equal(mask.sum(1).long(), kc)
+    assert float(kc.float().mean()) / n_pts > 0.45               # the planted 50 % model is found
+    for p in (0, 511, 1023):
+        c_np = corr[p].cpu().numpy()
+        Hw = oracle.ransac_hypothesis(c_np, oracle.ransac_sample(seed, p, int(hyp[p]), n_pts))
+        assert np.array_equal(H[p].cpu().numpy().view(np.uint32), Hw.view(np.uint32))
+        assert oracle.ransac_count(Hw, c_np, thr2) == int(kc[p])
+    # an id window around pair 0's winner, scored by the oracle: nothing in it beats the winner
+    lo = max(0, int(hyp[0]) - 500)
+    sub = corr[:1].contiguous()
+    win = oracle.ransac(sub.cpu().numpy(), n_hyp, seed, thr2, hyp_begin=lo, hyp_count=1000)
+    got = api.ransac_keys(sub, n_hyp, seed, thr2, None, lo, 1000).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, win) and int(win[0]) == int(full[0])
+    try:
+        for hpt, mode in ((4, 1), (2, 2), (4, 2), (2, 0)):
+            assert sks.c.sks_cuda_set_ransac_tuning(hpt, 8, mode) == 0
+            assert torch.equal(api.ransac_keys(corr[:128], n_hyp, seed, thr2), full[:128]), (hpt, mode)
+    finally:
+        sks.c.sks_cuda_set_ransac_tuning(2, 8, 1)
