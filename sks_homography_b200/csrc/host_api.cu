@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <cstring>
 #include <mutex>
+#include <condition_variable>
+#include <deque>
 #include <thread>
 #include <vector>
 
@@ -151,22 +153,82 @@ bool is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+// Persistent memcpy workers for the pageable staging path: spawning threads per copy costs
+// about as much as copying a few MiB, and the in- and out-stagers copy at the same time.
+class CopyPool {
+public:
+    static CopyPool& get()
+    {
+        static CopyPool* p = new CopyPool();   // leaked on purpose: workers may outlive static destructors
+        return *p;
+    }
+    // copy [src, src+bytes) to dst in slices of >= 1 MiB on up to `max_parts` workers; blocks
+    void copy(void* dst, const void* src, size_t bytes, unsigned max_parts)
+    {
+        const unsigned parts = (unsigned)std::min<size_t>(std::min<size_t>(max_parts, workers_.size()),
+                                                          bytes / (1u << 20) + 1);
+        if (parts <= 1 || workers_.empty()) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        Job job;
+        job.left = (int)parts;
+        const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            for (unsigned t = 0; t < parts; ++t) {
+                const size_t lo = std::min(bytes, per * t), hi = (t + 1 == parts) ? bytes : std::min(bytes, lo + per);
+                q_.push_back(Task{(char*)dst + lo, (const char*)src + lo, hi - lo, &job});
+            }
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> g(job.m);
+        job.cv.wait(g, [&] { return job.left == 0; });
+    }
+
+private:
+    struct Job {
+        std::mutex m;
+        std::condition_variable cv;
+        int left = 0;
+    };
+    struct Task {
+        char* dst;
+        const char* src;
+        size_t bytes;
+        Job* job;
+    };
+    CopyPool()
+    {
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        const unsigned n = std::min(16u, hw);
+        for (unsigned i = 0; i < n; ++i)
+            workers_.emplace_back([this] { loop(); }).detach();
+    }
+    void loop()
+    {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return !q_.empty(); });
+                t = q_.front();
+                q_.pop_front();
+            }
+            if (t.bytes) std::memcpy(t.dst, t.src, t.bytes);
+            std::lock_guard<std::mutex> g(t.job->m);
+            if (--t.job->left == 0) t.job->cv.notify_one();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Task> q_;
+    std::vector<std::thread> workers_;
+};
+
 void parallel_copy(void* dst, const void* src, size_t bytes)
 {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, hw), bytes / (4u << 20) + 1);
-    if (nt <= 1) {
-        std::memcpy(dst, src, bytes);
-        return;
-    }
-    std::vector<std::thread> th;
-    const size_t per = ((bytes / nt) + 63) & ~size_t(63);
-    for (unsigned t = 0; t < nt; ++t) {
-        const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, lo + per);
-        if (lo < hi)
-            th.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
-    }
-    for (auto& x : th) x.join();
+    CopyPool::get().copy(dst, src, bytes, 8);
 }
 
 // Generic pipeline.  in[k] (k < n_in) are host arrays of in_elems[k] elements
@@ -177,18 +239,110 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
                   Launch launch)
 {
     CK(cudaSetDevice(dev));
-    const int64_t cap = g_chunk_bytes.load() / (8 * (int64_t)sizeof(T));
-    const int64_t floor_q = std::min<int64_t>(cap, (8ll << 20) / (8 * (int64_t)sizeof(T)));
-    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, std::min(cap, std::max(floor_q, (n + 7) / 8))));
     bool stage_in = false;
     for (int k = 0; k < n_in; ++k) stage_in = stage_in || !is_pinned(in[k]);
     const bool stage_out = !is_pinned(out);
+    // staged (pageable) batches use smaller chunks: the two host memcpys overlap the DMA at a
+    // finer grain and the pipeline fills sooner
+    const int64_t cap_bytes = (stage_in || stage_out) ? std::min<int64_t>(g_chunk_bytes.load(), 16ll << 20)
+                                                      : g_chunk_bytes.load();
+    const int64_t cap = cap_bytes / (8 * (int64_t)sizeof(T));
+    const int64_t floor_q = std::min<int64_t>(cap, (8ll << 20) / (8 * (int64_t)sizeof(T)));
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, std::min(cap, std::max(floor_q, (n + 7) / 8))));
     HostCtx* c = nullptr;
     if (int rc = get_ctx(dev, &c)) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     if (int rc = ensure_capacity(c, chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T),
                                  stage_in, stage_out))
         return rc;
+
+    if (stage_in || stage_out) {
+        // Pageable caller buffers: three actors so that the memcpy into the pinned ring, the
+        // DMA + kernel, and the memcpy out of the ring all run at the same time instead of
+        // taking turns on one host thread --
+        //   in-stager  : chunk ci -> slot's pinned inputs (waits until the slot was drained)
+        //   this thread: H2D, kernel, D2H, event on the slot's stream (waits for the in-stager)
+        //   out-stager : waits for the event, copies the slot's pinned output to the caller
+        // Chunks complete in order, so three monotonic counters are the whole protocol.
+        const int64_t n_chunks = (n + chunk - 1) / chunk;
+        std::mutex m;
+        std::condition_variable cv;
+        int64_t staged = 0, enqueued = 0, freed = 0;     // chunks that passed each stage
+        std::atomic<int> err{SKS_OK};
+        auto fail = [&](int rc) {
+            int ok = SKS_OK;
+            err.compare_exchange_strong(ok, rc);
+            std::lock_guard<std::mutex> g(m);
+            cv.notify_all();
+        };
+        std::thread in_stager([&] {
+            cudaSetDevice(dev);
+            for (int64_t ci = 0; ci < n_chunks && err.load() == SKS_OK; ++ci) {
+                {
+                    std::unique_lock<std::mutex> g(m);     // slot reuse: chunk ci - kRing must be drained
+                    cv.wait(g, [&] { return freed >= ci - kRing + 1 || err.load() != SKS_OK; });
+                }
+                if (err.load() != SKS_OK) break;
+                Slot& sl = c->slot[ci % kRing];
+                const int64_t off = ci * chunk, cnt = std::min(chunk, n - off);
+                if (stage_in)
+                    for (int k = 0; k < n_in; ++k)
+                        parallel_copy(sl.p_in[k], in[k] + off * in_elems[k],
+                                      (size_t)cnt * in_elems[k] * sizeof(T));
+                std::lock_guard<std::mutex> g(m);
+                staged = ci + 1;
+                cv.notify_all();
+            }
+        });
+        std::thread out_stager([&] {
+            cudaSetDevice(dev);
+            for (int64_t ci = 0; ci < n_chunks && err.load() == SKS_OK; ++ci) {
+                {
+                    std::unique_lock<std::mutex> g(m);
+                    cv.wait(g, [&] { return enqueued > ci || err.load() != SKS_OK; });
+                }
+                if (err.load() != SKS_OK) break;
+                Slot& sl = c->slot[ci % kRing];
+                const cudaError_t e = cudaEventSynchronize(sl.done);
+                if (e != cudaSuccess) { fail((int)e); break; }
+                const int64_t off = ci * chunk, cnt = std::min(chunk, n - off);
+                if (stage_out)
+                    parallel_copy(out + off * 9, sl.p_out, (size_t)cnt * 9 * sizeof(T));
+                std::lock_guard<std::mutex> g(m);
+                freed = ci + 1;
+                cv.notify_all();
+            }
+        });
+        auto enqueue = [&](int64_t ci) -> int {
+            Slot& sl = c->slot[ci % kRing];
+            const int64_t off = ci * chunk, cnt = std::min(chunk, n - off);
+            for (int k = 0; k < n_in; ++k) {
+                const size_t bytes = (size_t)cnt * in_elems[k] * sizeof(T);
+                const T* hsrc = stage_in ? static_cast<const T*>(sl.p_in[k]) : in[k] + off * in_elems[k];
+                CK(cudaMemcpyAsync(sl.d_in[k], hsrc, bytes, cudaMemcpyHostToDevice, sl.stream));
+            }
+            if (int rc = launch(sl, cnt)) return rc;
+            T* hdst = stage_out ? static_cast<T*>(sl.p_out) : out + off * 9;
+            CK(cudaMemcpyAsync(hdst, sl.d_out, (size_t)cnt * 9 * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+            CK(cudaEventRecord(sl.done, sl.stream));
+            return SKS_OK;
+        };
+        for (int64_t ci = 0; ci < n_chunks && err.load() == SKS_OK; ++ci) {
+            {
+                std::unique_lock<std::mutex> g(m);
+                cv.wait(g, [&] { return staged > ci || err.load() != SKS_OK; });
+            }
+            if (err.load() != SKS_OK) break;
+            if (int rc = enqueue(ci)) { fail(rc); break; }
+            std::lock_guard<std::mutex> g(m);
+            enqueued = ci + 1;
+            cv.notify_all();
+        }
+        in_stager.join();
+        out_stager.join();
+        if (err.load() != SKS_OK) cudaDeviceSynchronize();   // nothing of this batch left in flight
+        return err.load();
+    }
 
     auto drain = [&](Slot& s) -> int {   // finish the chunk this slot last produced
         if (s.pending_off < 0) return SKS_OK;
