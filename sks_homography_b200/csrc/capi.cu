@@ -335,12 +335,13 @@ int launch_warp_grid(const float* H, const float* tar, const float* M, RectParam
     const GridSpec g{x0, y0, dx, dy, gw, gh};
     const int64_t m = (int64_t)gw * gh;
     if (m >= (int64_t)1 << 31) return SKS_ERR_INVALID_ARG;
-    // about 8-16 points per thread: group = largest power of two <= m/8 (1..256); beyond
-    // 256 x 16 points, several CTAs per sample
-    WarpSplit ws{1, 1, 0, 0};
-    while (ws.group < 256 && (int64_t)ws.group * 16 <= m) ws.group *= 2;
-    if (ws.group == 256) ws.parts = (int32_t)((m + 4095) / 4096);
-    const uint32_t stride = 2u * (uint32_t)ws.group * (uint32_t)ws.parts;
+    // about 16-32 points per thread (4 per iteration), which keeps the per-warp cost of
+    // re-solving the sample's homography below 10 % in the fused form: group = largest power
+    // of two <= m/16 (1..256); beyond 256 x 32 points, several CTAs per sample
+    WarpSplit ws{1, 1, 0, 0, (m % 4 == 0 && aligned32(out)) ? 1 : 0};
+    while (ws.group < 256 && (int64_t)ws.group * 32 <= m) ws.group *= 2;
+    if (ws.group == 256) ws.parts = (int32_t)((m + 8191) / 8192);
+    const uint32_t stride = 4u * (uint32_t)ws.group * (uint32_t)ws.parts;
     ws.step_i = stride % (uint32_t)gw;
     ws.step_j = stride / (uint32_t)gw;
     const int64_t per_cta = 256 / ws.group;

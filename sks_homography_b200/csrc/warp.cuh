@@ -12,8 +12,8 @@
 //                                               normalisation style, MOD/ACA_SKS.cpp:94-98)
 // Bound: HBM writes, 8 bytes per grid point (the 32-byte corner read per sample and the
 // 47-flop solve are noise next to gh*gw*8 bytes).  Every thread of a sample's group re-solves
-// the sample's homography (cheaper than a shared-memory broadcast plus barrier) and emits two
-// neighbouring grid points as one 16-byte store per iteration.
+// the sample's homography (cheaper than a shared-memory broadcast plus barrier) and emits four
+// neighbouring grid points as one 32-byte store per iteration.
 #pragma once
 #include <cstdint>
 
@@ -37,15 +37,37 @@ __device__ __forceinline__ float2 warp_point(const float (&h)[9], float x, float
 }
 
 // Work split: a sample's gh*gw points are covered by a GROUP of `group` threads (a power of
-// two, 1..256; `parts` > 1 CTAs per sample only for grids beyond 256 threads x 16 points), so
-// that every thread emits roughly 8-16 points whatever the grid size: small grids pack many
-// samples into one CTA, large grids loop.  The (i, j) grid position advances incrementally
-// (step_i = stride mod gw, step_j = stride / gw, host-computed): one 32-bit division per thread.
+// two, 1..256; `parts` > 1 CTAs per sample only for grids beyond 256 threads x 32 points), so
+// that every thread emits roughly 16-32 points whatever the grid size: small grids pack many
+// samples into one CTA, large grids loop.  A thread takes FOUR consecutive points per
+// iteration: one 32-bit division locates the run, the row terms h1*y+h2, h4*y+h5, h7*y+h8
+// are computed once per row, and the 32 bytes leave as one 256-bit store (sm_100 STG.256)
+// when every sample block is 32-byte aligned (gh*gw a multiple of 4).
 struct WarpSplit {
     int32_t group;        // threads per sample inside a CTA (divides 256)
     int32_t parts;        // CTAs per sample (1 unless group == 256)
-    uint32_t step_i, step_j;
+    uint32_t step_i, step_j;   // (4 * group * parts) mod gw, div gw
+    int32_t vec;          // 1: gh*gw is a multiple of 4 and out is 32-byte aligned -> 256-bit stores
 };
+
+struct RowTerms {
+    float au, av, aw;
+};
+
+__device__ __forceinline__ RowTerms warp_row(const float (&h)[9], float y)
+{
+    return RowTerms{__fmaf_rn(h[1], y, h[2]), __fmaf_rn(h[4], y, h[5]), __fmaf_rn(h[7], y, h[8])};
+}
+
+// same bits as warp_point(h, x, y) with the y terms hoisted
+__device__ __forceinline__ float2 warp_point_row(const float (&h)[9], const RowTerms& r, float x)
+{
+    const float u = __fmaf_rn(h[0], x, r.au);
+    const float v = __fmaf_rn(h[3], x, r.av);
+    const float w = __fmaf_rn(h[6], x, r.aw);
+    const float q = __frcp_rn(w);
+    return make_float2(__fmul_rn(u, q), __fmul_rn(v, q));
+}
 
 // FUSED: homographies come from ACA-rect on tar (H == nullptr), else they are read from H[n][9]
 template <bool FUSED>
@@ -59,9 +81,9 @@ k_warp_grid(const float* __restrict__ H, const float* __restrict__ tar, const fl
     if (s >= n)
         return;
     const uint32_t lane = (uint32_t)(blockIdx.x % ws.parts) * 256u + (uint32_t)(tid % ws.group);
-    const uint32_t m = (uint32_t)g.gw * (uint32_t)g.gh;
-    const uint32_t stride = 2u * (uint32_t)ws.group * (uint32_t)ws.parts;
-    uint32_t p = 2u * lane;
+    const uint32_t m = (uint32_t)g.gw * (uint32_t)g.gh, gw = (uint32_t)g.gw;
+    const uint32_t stride = 4u * (uint32_t)ws.group * (uint32_t)ws.parts;
+    uint32_t p = 4u * lane;
     if (p >= m)
         return;
     float h[9];
@@ -80,30 +102,39 @@ k_warp_grid(const float* __restrict__ H, const float* __restrict__ tar, const fl
             h[k] = __ldg(H + 9 * s + k);
     }
     float* o = out + 2 * (int64_t)m * s;
-    const bool vec = (m & 1u) == 0;      // every sample block then starts 16-byte aligned
-    uint32_t j = p / (uint32_t)g.gw, i = p - j * (uint32_t)g.gw;
+    const bool vec = ws.vec != 0;        // every sample block then starts 32-byte aligned
+    uint32_t j = p / gw, i = p - j * gw;
     for (; p < m; p += stride) {
-        const float2 q0 = warp_point(h, __fmaf_rn((float)i, g.dx, g.x0), __fmaf_rn((float)j, g.dy, g.y0));
-        if (p + 1 < m) {
-            const bool wrap = i + 1 == (uint32_t)g.gw;
-            const uint32_t i1 = wrap ? 0u : i + 1, j1 = wrap ? j + 1 : j;
-            const float2 q1 = warp_point(h, __fmaf_rn((float)i1, g.dx, g.x0), __fmaf_rn((float)j1, g.dy, g.y0));
-            if (vec) {
-                Chunk16 c;
-                c.w[0] = __float_as_uint(q0.x); c.w[1] = __float_as_uint(q0.y);
-                c.w[2] = __float_as_uint(q1.x); c.w[3] = __float_as_uint(q1.y);
-                stg_stream(o + 2 * (size_t)p, c);
-            } else {
-                o[2 * (size_t)p] = q0.x; o[2 * (size_t)p + 1] = q0.y;
-                o[2 * (size_t)p + 2] = q1.x; o[2 * (size_t)p + 3] = q1.y;
+        RowTerms r = warp_row(h, __fmaf_rn((float)j, g.dy, g.y0));
+        float2 q[4];
+        uint32_t ii = i, jj = j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            q[k] = warp_point_row(h, r, __fmaf_rn((float)ii, g.dx, g.x0));
+            if (++ii == gw) {            // run crosses into the next row
+                ii = 0;
+                ++jj;
+                r = warp_row(h, __fmaf_rn((float)jj, g.dy, g.y0));
             }
+        }
+        if (vec) {
+            Chunk32 c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                c.w[2 * k] = __float_as_uint(q[k].x);
+                c.w[2 * k + 1] = __float_as_uint(q[k].y);
+            }
+            stg_stream32(o + 2 * (size_t)p, c);
         } else {
-            o[2 * (size_t)p] = q0.x; o[2 * (size_t)p + 1] = q0.y;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (p + k < m)
+                    *reinterpret_cast<float2*>(o + 2 * (size_t)(p + k)) = q[k];
         }
         i += ws.step_i;
         j += ws.step_j;
-        if (i >= (uint32_t)g.gw) {
-            i -= (uint32_t)g.gw;
+        if (i >= gw) {
+            i -= gw;
             ++j;
         }
     }

@@ -21,7 +21,7 @@ def time_ms(fn, it=20):
     return e0.elapsed_time(e1) / it
 
 
-for n, g in ((4096, 128), (65536, 32), (1 << 20, 8), (1 << 22, 2)):
+for n, g in ((4096, 128), (16384, 128), (65536, 32), (262144, 32), (1 << 20, 8), (1 << 22, 8), (1 << 22, 2)):
     _, tar = api.synth_quads(n, seed=11, device=dev)
     out = torch.empty((n, g, g, 2), dtype=torch.float32, device=dev)
     H = torch.empty((n, 9), dtype=torch.float32, device=dev)
