@@ -53,6 +53,13 @@ __device__ __forceinline__ Chunk16 ldg_stream(const void* p)
                  : "l"(p));
     return c;
 }
+// read-once 32-bit value (sample lists): keep it out of L1, which holds the gather table
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void stg_stream(void* p, const Chunk16& c)
 {
 #if SKS_ST_HINT == 1

@@ -312,7 +312,7 @@ k_gather_solve(const T* __restrict__ pool, uint32_t pool_size, const uint32_t* _
         for (int k = 0; k < 4; ++k) {
             uint32_t r;
             if (rand4 != nullptr)
-                r = __ldg(rand4 + (int64_t)k * n + i);
+                r = ldg_stream_u32(rand4 + (int64_t)k * n + i);   // streamed once: do not evict the pool from L1
             else {
                 uint64_t z = key ^ ((uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)k);
                 z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
