@@ -109,6 +109,7 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
     if (n == 0) return SKS_OK;   // empty batch: nothing to enqueue (buffers may be NULL)
     if (!aligned16(H) || !aligned16(tar) || (src && !aligned16(src)) || (M && !aligned16(M)))
         return SKS_ERR_UNALIGNED;
+    if (n > ((int64_t)1 << 36)) return SKS_ERR_INVALID_ARG;   // grid.x limit (2^31 - 1 CTAs of >= 32 quadruples)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool normalize = (flags & SKS_FLAG_NORMALIZE) != 0;
 
