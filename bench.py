@@ -359,6 +359,10 @@ def main():
                "h2d_bytes_per_step": ne * in_elems * esz, "d2h_bytes_per_step": ne * 9 * esz,
                "steps": args.e2e_steps, "quadruples_per_step_per_gpu": ne,
                "api": "sks_host_* (pinned host buffers, chunked H2D/kernel/D2H ring)",
+               "bound": "PCIe: every homography moves %d B host->device and %d B back; at the ~50 GB/s a Gen5 x16 "
+                        "link sustains with both directions busy that is a ceiling of ~%.2f G H/s per GPU, "
+                        "whatever the kernel does (DESIGN.md section 3, host-pointer path)"
+                        % (in_elems * esz, 9 * esz, 50.0 / (in_elems * esz)),
                "numa_binding": args.numa}
         # the host path must give the same bytes as the device path
         if not torch.equal(hH.view(torch.int32 if dt == "f32" else torch.int64),
