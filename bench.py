@@ -591,6 +591,10 @@ def run_ransac(args, api, L, dev, rank, world, local):
         h_cnt = torch.empty(P, dtype=torch.int32).pin_memory()
 
         def e2e_step():
+            if world == 1 and reducer is None:      # the host-pointer C-ABI call, as a C++ caller would make it
+                H, c, _, _ = api.ransac_host(h_corr, n_hyp, args.seed, thr2)
+                h_H.copy_(H); h_cnt.copy_(c)
+                return
             d_corr.copy_(h_corr, non_blocking=True)
             keys.zero_()
             api.ransac_keys(d_corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys)
@@ -616,6 +620,8 @@ def run_ransac(args, api, L, dev, rank, world, local):
         e2e_ms = float(t.item()) / args.e2e_steps
         e2e = {"value": P * n_hyp / (e2e_ms * 1e-3), "unit": "hypotheses/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": corr.numel() * 4, "d2h_bytes_per_step": P * 9 * 4 + P * 4,
+               "api": "sks_host_ransac_aca_f32 (host matches in, models out)" if world == 1 and reducer is None
+                      else "per-rank H2D + sks_cuda_ransac_aca_f32 on the rank's hypothesis shard + max-reduce + finalize",
                "models_equal_device_path": bool(torch.equal(h_H, res["H"].cpu()))}
 
     # CPU baseline: the oracle's scalar port of the same definition on one host core, on a bounded

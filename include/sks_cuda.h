@@ -128,6 +128,15 @@ int sks_host_aca_rect_f32(const float *tar, const float *M, float mx, float my, 
                           float ratio, float *H, int64_t n, int flags);
 int sks_host_aca_rect_f64(const double *tar, const double *M, double mx, double my,
                           double width, double ratio, double *H, int64_t n, int flags);
+/* Fused ACA-RANSAC for callers that hold their matches in host memory (corr
+ * [n_pairs][n_pts][4], optional samples [n_pairs][n_hyp][4]): copies in, scores hypothesis
+ * ids [0, n_hyp), rebuilds the winners and copies out H_best [n_pairs][9] and, when
+ * non-NULL, inlier_count [n_pairs], inlier_mask [n_pairs][n_pts], best_key [n_pairs].
+ * Synchronous; same definitions as sks_cuda_ransac_aca_f32 / _finalize_f32 below. */
+int sks_host_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                            const uint32_t *samples, uint32_t n_hyp, uint64_t seed, float thr2,
+                            float *H_best, uint32_t *inlier_count, uint8_t *inlier_mask,
+                            unsigned long long *best_key);
 /* In-process multi-GPU driver for the host-pointer entry points: shard every batch
  * contiguously over `count` GPUs (devices 0..count-1; 0 = all visible; default 1 =
  * the current device only), one host thread and one PCIe link per GPU, no

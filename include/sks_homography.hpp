@@ -68,6 +68,17 @@ inline int runKernel_ACA_rect_double(double* tar, double M_x, double M_y, double
     return sks_host_aca_rect_f64(tar, nullptr, M_x, M_y, width, ratio_rec, result, n, SKS_FLAG_NORMALIZE);
 }
 
+// New here (nothing like it in the reference): the fused ACA-RANSAC over host buffers.
+// corr[n_pairs][n_pts][4] = (x, y, X, Y); the n_hyp minimal samples per pair come from the
+// counter RNG keyed by seed; optional outputs may be null.
+inline int runRansac_ACA(const float* corr, std::int64_t n_pairs, std::int32_t n_pts, std::uint32_t n_hyp,
+                         std::uint64_t seed, float thr2, float* H_best, std::uint32_t* inlier_count = nullptr,
+                         std::uint8_t* inlier_mask = nullptr)
+{
+    return sks_host_ransac_aca_f32(corr, n_pairs, n_pts, nullptr, n_hyp, seed, thr2, H_best, inlier_count,
+                                   inlier_mask, nullptr);
+}
+
 }  // namespace sks
 
 // The reference keeps its competitor solvers in namespace cv; the one that is

@@ -59,6 +59,7 @@ _SIGS = {
     "sks_host_ge_f64": (_int, [_vp, _vp, _vp, _i64, _int]),
     "sks_host_aca_rect_f32": (_int, [_vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _int]),
     "sks_host_aca_rect_f64": (_int, [_vp, _vp, _f64, _f64, _f64, _f64, _vp, _i64, _int]),
+    "sks_host_ransac_aca_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u64, _f32, _vp, _vp, _vp, _vp]),
     "sks_host_set_device_count": (_int, [_int]),
     "sks_host_set_chunk_bytes": (_int, [_i64]),
     "sks_host_alloc_pinned": (_int, [C.POINTER(_vp), _i64]),

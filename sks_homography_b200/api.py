@@ -320,6 +320,26 @@ def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     return out
 
 
+def ransac_host(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
+                samples: torch.Tensor | None = None, want_mask: bool = False):
+    """Whole estimate from HOST tensors through sks_host_ransac_aca_f32: corr [P, n_pts, 4] fp32 in
+    host memory (pinned or pageable) -> (H [P,9], count [P], mask [P,n_pts] | None, keys [P])."""
+    L = lib()
+    if corr.is_cuda or corr.dtype != torch.float32:
+        raise ValueError("ransac_host takes float32 host tensors")
+    corr = corr.contiguous()
+    P, n_pts, _ = corr.shape
+    H = torch.empty((P, 9), dtype=torch.float32)
+    cnt = torch.empty(P, dtype=torch.int32)
+    keys = torch.empty(P, dtype=torch.int64)
+    mask = torch.empty((P, n_pts), dtype=torch.uint8) if want_mask else None
+    if samples is not None:
+        samples = samples.contiguous()
+    L.check(L.c.sks_host_ransac_aca_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed, thr2, _ptr(H),
+                                        _ptr(cnt), _ptr(mask), _ptr(keys)), "sks_host_ransac_aca_f32")
+    return H, cnt, mask, keys
+
+
 def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys: torch.Tensor,
                     samples: torch.Tensor | None = None, want_mask: bool = False):
     L = lib()

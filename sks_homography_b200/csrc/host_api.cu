@@ -485,6 +485,81 @@ int sks_host_aca_rect_f64(const double* tar, const double* M, double mx, double 
     return host_rect<double>(sks_cuda_aca_rect_f64, tar, M, mx, my, width, ratio, H, n, flags);
 }
 
+// Whole robust estimate for callers that hold their matches in host memory: H2D of the
+// correspondences (and of an explicit sample list, if any), fused scoring of all hypothesis
+// ids, finalize, D2H of models / counts / masks -- on the current device.  Device buffers
+// and the stream are kept per device and only ever grow (an allocation per call costs more
+// than the copies: 19 ms of a 122 ms call at 1024 pairs x 4096 matches).
+struct RansacHostCtx {
+    int device = -1;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    void* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // corr, H, cnt, key, samples, mask
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+};
+static std::vector<RansacHostCtx*> g_ransac_ctx;      // guarded by g_mu
+
+int sks_host_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts, const uint32_t* samples,
+                            uint32_t n_hyp, uint64_t seed, float thr2, float* H_best,
+                            uint32_t* inlier_count, uint8_t* inlier_mask, unsigned long long* best_key)
+{
+    if (corr == nullptr || H_best == nullptr || n_pairs < 0 || n_pts <= 0) return SKS_ERR_INVALID_ARG;
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        cudaGetLastError();
+        return SKS_ERR_NO_DEVICE;
+    }
+    if (n_pairs == 0) return SKS_OK;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    RansacHostCtx* c = nullptr;
+    {
+        std::lock_guard<std::mutex> table(g_mu);
+        for (RansacHostCtx* x : g_ransac_ctx)
+            if (x->device == dev) c = x;
+        if (c == nullptr) {
+            c = new RansacHostCtx();
+            c->device = dev;
+            CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            g_ransac_ctx.push_back(c);
+        }
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t need[6] = {(size_t)n_pairs * n_pts * 4 * sizeof(float), (size_t)n_pairs * 9 * sizeof(float),
+                            (size_t)n_pairs * sizeof(uint32_t), (size_t)n_pairs * sizeof(unsigned long long),
+                            samples ? (size_t)n_pairs * n_hyp * 4 * sizeof(uint32_t) : 0,
+                            inlier_mask ? (size_t)n_pairs * n_pts : 0};
+    for (int k = 0; k < 6; ++k)
+        if (need[k] > c->cap[k]) {
+            if (c->buf[k]) CK(cudaFree(c->buf[k]));
+            c->buf[k] = nullptr;
+            c->cap[k] = 0;
+            CK(cudaMalloc(&c->buf[k], need[k]));
+            c->cap[k] = need[k];
+        }
+    cudaStream_t st = c->stream;
+    float* d_corr = static_cast<float*>(c->buf[0]);
+    float* d_H = static_cast<float*>(c->buf[1]);
+    uint32_t* d_cnt = static_cast<uint32_t*>(c->buf[2]);
+    unsigned long long* d_key = static_cast<unsigned long long*>(c->buf[3]);
+    uint32_t* d_samp = samples ? static_cast<uint32_t*>(c->buf[4]) : nullptr;
+    uint8_t* d_mask = inlier_mask ? static_cast<uint8_t*>(c->buf[5]) : nullptr;
+    CK(cudaMemcpyAsync(d_corr, corr, need[0], cudaMemcpyHostToDevice, st));
+    if (samples) CK(cudaMemcpyAsync(d_samp, samples, need[4], cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_key, 0, need[3], st));
+    if (int rc = sks_cuda_ransac_aca_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, 0, n_hyp, seed, thr2, d_key, st))
+        return rc;
+    if (int rc = sks_cuda_ransac_finalize_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, seed, thr2, d_key, d_H,
+                                              d_cnt, d_mask, st))
+        return rc;
+    CK(cudaMemcpyAsync(H_best, d_H, need[1], cudaMemcpyDeviceToHost, st));
+    if (inlier_count) CK(cudaMemcpyAsync(inlier_count, d_cnt, need[2], cudaMemcpyDeviceToHost, st));
+    if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, d_mask, need[5], cudaMemcpyDeviceToHost, st));
+    if (best_key) CK(cudaMemcpyAsync(best_key, d_key, need[3], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SKS_OK;
+}
+
 int sks_host_alloc_pinned(void** ptr, int64_t bytes)
 {
     if (ptr == nullptr || bytes < 0) return SKS_ERR_INVALID_ARG;
@@ -520,6 +595,17 @@ int sks_cuda_shutdown(void)
     std::lock_guard<std::mutex> lk(g_mu);
     for (HostCtx* c : g_ctx) free_ctx(c);
     g_ctx.clear();
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (RansacHostCtx* c : g_ransac_ctx) {
+        cudaSetDevice(c->device);
+        for (void* b : c->buf)
+            if (b) cudaFree(b);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+    }
+    g_ransac_ctx.clear();
+    cudaSetDevice(prev);
     return SKS_OK;
 }
 

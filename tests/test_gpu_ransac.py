@@ -144,3 +144,21 @@ def test_peer_reducer_single_rank_epochs(api, cuda):
             assert torch.equal(keys, want) and not red.timed_out()
     finally:
         red.close()
+
+
+def test_host_pointer_entry_point(api, oracle, cuda):
+    """sks_host_ransac_aca_f32: matches in host memory in, models / counts / masks / keys out."""
+    P, n_pts, n_hyp = 3, 2000, 1500
+    corr = api.synth_corr(P, n_pts, seed=8, device=cuda).cpu()
+    H, cnt, mask, keys = api.ransac_host(corr, n_hyp, seed=4, thr2=2.25, want_mask=True)
+    want = oracle.ransac(corr.numpy(), n_hyp, seed=4, thr2=2.25)
+    assert np.array_equal(u64(keys), want)
+    kc, hyp = api.decode_keys(keys)
+    assert torch.equal(cnt.long(), kc) and torch.equal(mask.sum(1).long(), kc)
+    for p in range(P):
+        Hw = oracle.ransac_hypothesis(corr[p].numpy(), oracle.ransac_sample(4, p, int(hyp[p]), n_pts))
+        assert np.array_equal(H[p].numpy().view(np.uint32), Hw.view(np.uint32))
+    samples = torch.from_numpy(np.array([[oracle.ransac_sample(4, p, j, n_pts) for j in range(n_hyp)]
+                                         for p in range(P)], dtype=np.uint32).view(np.int32))
+    _, _, _, k2 = api.ransac_host(corr.pin_memory(), n_hyp, seed=0, thr2=2.25, samples=samples)
+    assert torch.equal(k2, keys)
