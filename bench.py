@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--hpt", type=int, default=0, help="RANSAC hypotheses per thread (2|4)")
     ap.add_argument("--rounds", type=int, default=8, help="RANSAC rounds per CTA")
     ap.add_argument("--packed", type=int, default=-1, help="RANSAC FFMA2 scoring (0|1)")
+    ap.add_argument("--ransac-shard", default="hypotheses", choices=["hypotheses", "pairs"],
+                    help="multi-GPU RANSAC: shard the hypothesis ids of every pair (one max all-reduce; "
+                         "north_star's variant) or the image pairs (no collective at all)")
     ap.add_argument("--peer-reduce", action="store_true",
                     help="RANSAC: merge the winners with the hand-written NVLink peer max-reduce "
                          "instead of the NCCL all-reduce")
@@ -504,20 +507,32 @@ def run_ransac(args, api, L, dev, rank, world, local):
 
     P, n_pts, n_hyp = args.pairs, args.points, args.hyps
     thr2 = 2.25
-    corr = api.synth_corr(P, n_pts, seed=args.seed, inlier_permille=500, noise=0.5, device=dev)
-    hb, hc = sd.shard_range(n_hyp, rank, world)
-    keys = torch.zeros(P, dtype=torch.int64, device=dev)
+    by_pairs = args.ransac_shard == "pairs" and world > 1
+    if by_pairs:
+        # SURVEY.md 8(e) variant B: this rank owns pairs [pb, pb + pc) and scores every hypothesis
+        # id of them; nothing is exchanged (the throughput-optimal split for many pairs)
+        pb, pc = sd.shard_range(P, rank, world)
+        corr = api.synth_corr(pc, n_pts, seed=args.seed, inlier_permille=500, noise=0.5, device=dev,
+                              pair_begin=pb)
+        hb, hc = 0, n_hyp
+    else:
+        pb, pc = 0, P
+        corr = api.synth_corr(P, n_pts, seed=args.seed, inlier_permille=500, noise=0.5, device=dev)
+        hb, hc = sd.shard_range(n_hyp, rank, world)
+    keys = torch.zeros(pc, dtype=torch.int64, device=dev)
     res = {}
-    reducer = sd.PeerReducer(P, dev) if args.peer_reduce else None
+    reducer = sd.PeerReducer(P, dev) if (args.peer_reduce and not by_pairs) else None
 
     def step():
         keys.zero_()
-        api.ransac_keys(corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys)
-        if reducer is not None:
+        api.ransac_keys(corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys, pair_begin=pb)
+        if by_pairs:
+            pass
+        elif reducer is not None:
             reducer.max_reduce_(keys)
         else:
             sd.merge_keys(keys)
-        res["H"], res["cnt"], _ = api.ransac_finalize(corr, n_hyp, args.seed, thr2, keys)
+        res["H"], res["cnt"], _ = api.ransac_finalize(corr, n_hyp, args.seed, thr2, keys, pair_begin=pb)
 
     def barrier():
         if world > 1:
@@ -565,13 +580,13 @@ def run_ransac(args, api, L, dev, rank, world, local):
     if rank == 0 and not args.no_cpu:
         from oracle.oracle import Oracle
         o = Oracle()
-        sel = [0, P // 2, P - 1]
+        sel = [0, pc // 2, pc - 1]
         sub = corr[sel].contiguous()
         nh = min(n_hyp, 2048)
         got = api.ransac_keys(sub, n_hyp, args.seed, thr2, None, 0, nh).cpu().numpy().view(np.uint64)
         want = o.ransac(sub.cpu().numpy(), nh, args.seed, thr2)      # same pair ids 0..2, hyps 0..nh-1
         full1 = None
-        if world > 1:
+        if world > 1 and not by_pairs:
             full1 = api.ransac_keys(sub, n_hyp, args.seed, thr2)
             k2 = torch.zeros(3, dtype=torch.int64, device=dev)
             for r in range(world):
@@ -587,8 +602,8 @@ def run_ransac(args, api, L, dev, rank, world, local):
     if not args.no_e2e:
         h_corr = corr.cpu().pin_memory()
         d_corr = torch.empty_like(corr)
-        h_H = torch.empty((P, 9), dtype=torch.float32).pin_memory()
-        h_cnt = torch.empty(P, dtype=torch.int32).pin_memory()
+        h_H = torch.empty((pc, 9), dtype=torch.float32).pin_memory()
+        h_cnt = torch.empty(pc, dtype=torch.int32).pin_memory()
 
         def e2e_step():
             if world == 1 and reducer is None:      # the host-pointer C-ABI call, as a C++ caller would make it
@@ -597,12 +612,14 @@ def run_ransac(args, api, L, dev, rank, world, local):
                 return
             d_corr.copy_(h_corr, non_blocking=True)
             keys.zero_()
-            api.ransac_keys(d_corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys)
-            if reducer is not None:
+            api.ransac_keys(d_corr, n_hyp, args.seed, thr2, None, hb, hc, out=keys, pair_begin=pb)
+            if by_pairs:
+                pass
+            elif reducer is not None:
                 reducer.max_reduce_(keys)
             else:
                 sd.merge_keys(keys)
-            H, c, _ = api.ransac_finalize(d_corr, n_hyp, args.seed, thr2, keys)
+            H, c, _ = api.ransac_finalize(d_corr, n_hyp, args.seed, thr2, keys, pair_begin=pb)
             h_H.copy_(H, non_blocking=True)
             h_cnt.copy_(c, non_blocking=True)
 
@@ -619,7 +636,7 @@ def run_ransac(args, api, L, dev, rank, world, local):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item()) / args.e2e_steps
         e2e = {"value": P * n_hyp / (e2e_ms * 1e-3), "unit": "hypotheses/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": corr.numel() * 4, "d2h_bytes_per_step": P * 9 * 4 + P * 4,
+               "h2d_bytes_per_step": corr.numel() * 4, "d2h_bytes_per_step": pc * 9 * 4 + pc * 4,
                "api": "sks_host_ransac_aca_f32 (host matches in, models out)" if world == 1 and reducer is None
                       else "per-rank H2D + sks_cuda_ransac_aca_f32 on the rank's hypothesis shard + max-reduce + finalize",
                "models_equal_device_path": bool(torch.equal(h_H, res["H"].cpu()))}
@@ -648,9 +665,10 @@ def run_ransac(args, api, L, dev, rank, world, local):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"fused ACA-RANSAC {P} pairs x {n_pts} matches x {n_hyp} hypotheses, "
-                                   f"hypotheses sharded over {world} GPU(s), "
-                                   + ("winners merged by NVLink peer atomics (csrc/peer.cuh)" if reducer
-                                      else "one int64 max all-reduce (NCCL)"),
+                                   + (f"image pairs sharded over {world} GPU(s), no collective" if by_pairs else
+                                      f"hypotheses sharded over {world} GPU(s), "
+                                      + ("winners merged by NVLink peer atomics (csrc/peer.cuh)" if reducer
+                                         else "one int64 max all-reduce (NCCL)")),
                        "thr2": thr2, "seed": args.seed,
                        "l2": "compute-bound; matches (64 KiB/pair) live in shared memory"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

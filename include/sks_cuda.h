@@ -203,6 +203,20 @@ int sks_cuda_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
                             const uint32_t *samples, uint32_t hyp_stride, uint32_t hyp_begin,
                             uint32_t hyp_count, uint64_t seed, float thr2,
                             unsigned long long *best_key, void *stream);
+/* The same on a SHARD of the image pairs (multi-GPU variant with zero communication:
+ * each GPU owns pairs [pair_begin, pair_begin + n_pairs)).  corr / samples / best_key point at
+ * the shard's first pair; pair_begin only keys the counter RNG, so a shard draws exactly
+ * the samples the same pairs get in an unsharded call. */
+int sks_cuda_ransac_aca_shard_f32(const float *corr, int64_t pair_begin, int64_t n_pairs,
+                                  int32_t n_pts, const uint32_t *samples, uint32_t hyp_stride,
+                                  uint32_t hyp_begin, uint32_t hyp_count, uint64_t seed,
+                                  float thr2, unsigned long long *best_key, void *stream);
+int sks_cuda_ransac_finalize_shard_f32(const float *corr, int64_t pair_begin, int64_t n_pairs,
+                                       int32_t n_pts, const uint32_t *samples,
+                                       uint32_t hyp_stride, uint64_t seed, float thr2,
+                                       const unsigned long long *best_key, float *H_best,
+                                       uint32_t *inlier_count, uint8_t *inlier_mask,
+                                       void *stream);
 /* Recompute the winning model of every pair from best_key (the sample list is
  * a pure function of the seed, so no H ever travels between GPUs): H_best
  * [n_pairs][9], inlier_count [n_pairs], optional inlier_mask [n_pairs][n_pts]. */

@@ -111,8 +111,9 @@ class Oracle:
         return int(self.lib.oracle_rng_u64(seed, ctr, lane))
 
     def ransac(self, corr, n_hyp: int, seed: int, thr2: float, samples=None, hyp_begin: int = 0,
-               hyp_count: int | None = None, want_counts: bool = False):
-        """corr [P, n_pts, 4] float32 -> best_key [P] uint64 (+ counts [P, hyp_count])."""
+               hyp_count: int | None = None, want_counts: bool = False, pair_begin: int = 0):
+        """corr [P, n_pts, 4] float32 -> best_key [P] uint64 (+ counts [P, hyp_count]).
+        pair_begin: global id of corr[0] when corr is a shard of the pairs (keys the sampler)."""
         corr = _c(corr, np.float32)
         P, n_pts, _ = corr.shape
         hyp_count = n_hyp - hyp_begin if hyp_count is None else hyp_count
@@ -122,7 +123,7 @@ class Oracle:
         if samples is not None:
             samples = _c(samples, np.uint32).reshape(P, n_hyp, 4)
             sp = _p(samples)
-        self.lib.oracle_ransac_aca_f32(_p(corr), C.c_int64(P), C.c_int32(n_pts), sp,
+        self.lib.oracle_ransac_aca_shard_f32(_p(corr), C.c_int64(pair_begin), C.c_int64(P), C.c_int32(n_pts), sp,
                                        C.c_uint32(hyp_begin), C.c_uint32(hyp_count),
                                        C.c_uint32(n_hyp), C.c_uint64(seed), C.c_float(thr2),
                                        _p(keys), _p(counts) if want_counts else None)

@@ -324,10 +324,12 @@ void oracle_ransac_hypothesis_f32(const float *corr, const uint32_t idx[4], floa
     oracle_aca_one_f32(s, t, H, 1);
 }
 
-void oracle_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
-                           const uint32_t *samples, uint32_t hyp_begin, uint32_t hyp_count,
-                           uint32_t hyp_stride, uint64_t seed, float thr2, uint64_t *best_key,
-                           uint32_t *counts_out)
+/* corr / samples / best_key / counts_out point at the first pair of a shard whose global pair
+ * ids are [pair_begin, pair_begin + n_pairs): the id only keys the sampler. */
+void oracle_ransac_aca_shard_f32(const float *corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
+                                 const uint32_t *samples, uint32_t hyp_begin, uint32_t hyp_count,
+                                 uint32_t hyp_stride, uint64_t seed, float thr2, uint64_t *best_key,
+                                 uint32_t *counts_out)
 {
     for (int64_t p = 0; p < n_pairs; ++p) {
         const float *c = corr + 4 * (size_t)n_pts * (size_t)p;
@@ -338,7 +340,7 @@ void oracle_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
             if (samples)
                 memcpy(idx, samples + 4 * ((size_t)p * hyp_stride + hyp), sizeof idx);
             else
-                oracle_ransac_sample(seed, p, hyp, n_pts, idx);
+                oracle_ransac_sample(seed, pair_begin + p, hyp, n_pts, idx);
             float H[9];
             oracle_ransac_hypothesis_f32(c, idx, H);
             const uint32_t cnt = oracle_ransac_count_f32(H, c, n_pts, thr2);
@@ -350,4 +352,13 @@ void oracle_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
         }
         best_key[p] = best;
     }
+}
+
+void oracle_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                           const uint32_t *samples, uint32_t hyp_begin, uint32_t hyp_count,
+                           uint32_t hyp_stride, uint64_t seed, float thr2, uint64_t *best_key,
+                           uint32_t *counts_out)
+{
+    oracle_ransac_aca_shard_f32(corr, 0, n_pairs, n_pts, samples, hyp_begin, hyp_count, hyp_stride, seed,
+                                thr2, best_key, counts_out);
 }

@@ -56,6 +56,10 @@ uint32_t oracle_ransac_count_f32(const float *H, const float *corr, int32_t n_pt
 void oracle_ransac_sample(uint64_t seed, int64_t pair, uint32_t hyp, int32_t n_pts,
                           uint32_t idx[4]);
 void oracle_ransac_hypothesis_f32(const float *corr, const uint32_t idx[4], float *H);
+void oracle_ransac_aca_shard_f32(const float *corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
+                                 const uint32_t *samples, uint32_t hyp_begin, uint32_t hyp_count,
+                                 uint32_t hyp_stride, uint64_t seed, float thr2, uint64_t *best_key,
+                                 uint32_t *counts_out);
 void oracle_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
                            const uint32_t *samples, uint32_t hyp_begin, uint32_t hyp_count,
                            uint32_t hyp_stride, uint64_t seed, float thr2, uint64_t *best_key,

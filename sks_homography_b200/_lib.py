@@ -75,6 +75,8 @@ _SIGS = {
                                         _i32, _i32, _vp, _vp]),
     "sks_cuda_curand_mrg32k3a_u32": (_int, [_vp, _i64, _u64, _vp]),
     "sks_cuda_ransac_aca_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u32, _u32, _u64, _f32, _vp, _vp]),
+    "sks_cuda_ransac_aca_shard_f32": (_int, [_vp, _i64, _i64, _i32, _vp, _u32, _u32, _u32, _u64, _f32, _vp, _vp]),
+    "sks_cuda_ransac_finalize_shard_f32": (_int, [_vp, _i64, _i64, _i32, _vp, _u32, _u64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "sks_cuda_ransac_finalize_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "sks_cuda_synth_quads_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _int, _int, _i64, _vp]),
     "sks_cuda_synth_quads_f64": (_int, [_vp, _vp, _i64, _i64, _u64, _int, _int, _i64, _vp]),

@@ -304,9 +304,11 @@ def curand_mrg32k3a(n: int, seed: int = 11, device="cuda", out: torch.Tensor | N
 # ------------------------------------------------------------------- RANSAC
 def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
                 samples: torch.Tensor | None = None, hyp_begin: int = 0,
-                hyp_count: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+                hyp_count: int | None = None, out: torch.Tensor | None = None,
+                pair_begin: int = 0) -> torch.Tensor:
     """Score hypothesis ids [hyp_begin, hyp_begin+hyp_count) of every pair and
-    max-combine into `out` (int64 view of the packed uint64 keys)."""
+    max-combine into `out` (int64 view of the packed uint64 keys).  pair_begin: global id of
+    corr[0] when `corr` is one rank's shard of the image pairs (keys the sampler only)."""
     L = lib()
     corr = corr.contiguous()
     P, n_pts, _ = corr.shape
@@ -314,9 +316,10 @@ def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     if out is None:
         out = torch.zeros(P, dtype=torch.int64, device=corr.device)
     with torch.cuda.device(corr.device):
-        L.check(L.c.sks_cuda_ransac_aca_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, hyp_begin,
-                                            hyp_count, seed, thr2, _ptr(out), _stream_ptr(corr)),
-                "sks_cuda_ransac_aca_f32")
+        L.check(L.c.sks_cuda_ransac_aca_shard_f32(_ptr(corr), pair_begin, P, n_pts, _ptr(samples), n_hyp,
+                                                  hyp_begin, hyp_count, seed, thr2, _ptr(out),
+                                                  _stream_ptr(corr)),
+                "sks_cuda_ransac_aca_shard_f32")
     return out
 
 
@@ -341,7 +344,7 @@ def ransac_host(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
 
 
 def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys: torch.Tensor,
-                    samples: torch.Tensor | None = None, want_mask: bool = False):
+                    samples: torch.Tensor | None = None, want_mask: bool = False, pair_begin: int = 0):
     L = lib()
     corr = corr.contiguous()
     P, n_pts, _ = corr.shape
@@ -349,8 +352,8 @@ def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys
     cnt = torch.empty(P, dtype=torch.int32, device=corr.device)
     mask = torch.empty((P, n_pts), dtype=torch.uint8, device=corr.device) if want_mask else None
     with torch.cuda.device(corr.device):
-        L.check(L.c.sks_cuda_ransac_finalize_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed,
-                                                 thr2, _ptr(keys), _ptr(H), _ptr(cnt), _ptr(mask),
+        L.check(L.c.sks_cuda_ransac_finalize_shard_f32(_ptr(corr), pair_begin, P, n_pts, _ptr(samples), n_hyp,
+                                                 seed, thr2, _ptr(keys), _ptr(H), _ptr(cnt), _ptr(mask),
                                                  _stream_ptr(corr)),
                 "sks_cuda_ransac_finalize_f32")
     return H, cnt, mask

@@ -393,11 +393,12 @@ int sks_cuda_curand_mrg32k3a_u32(uint32_t* out, int64_t n, uint64_t seed, void* 
     return finish_launch();
 }
 
-int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
-                            const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,
-                            uint32_t hyp_count, uint64_t seed, float thr2,
-                            unsigned long long* best_key, void* stream)
+int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
+                                  const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,
+                                  uint32_t hyp_count, uint64_t seed, float thr2,
+                                  unsigned long long* best_key, void* stream)
 {
+    if (pair_begin < 0) return SKS_ERR_INVALID_ARG;
     if (corr == nullptr || best_key == nullptr || n_pairs < 0 || n_pts <= 0)
         return SKS_ERR_INVALID_ARG;
     if (samples != nullptr && ((uint64_t)hyp_stride < (uint64_t)hyp_begin + hyp_count || !aligned16(samples)))
@@ -412,7 +413,7 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
     const int mode = g_ransac_packed.load();
     const int threads = g_ransac_threads.load();
     using Kern = void (*)(const float4*, int64_t, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
-                          uint32_t, uint32_t, uint64_t, float, unsigned long long*);
+                          uint32_t, uint32_t, uint64_t, float, unsigned long long*, int64_t);
 #define SKS_RANSAC_PICK(T)                                                                        \
     (mode == 2 ? (hpt == 4 ? k_ransac_aca<4, 2, T> : k_ransac_aca<2, 2, T>)                       \
      : mode == 1 ? (hpt == 4 ? k_ransac_aca<4, 1, T> : k_ransac_aca<2, 1, T>)                     \
@@ -437,10 +438,19 @@ int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
         dim3 grid(chunks, (unsigned)np);
         kern<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const float4*>(corr), p0, n_pts, tile_pts, samples, hyp_stride, hyp_begin,
-            hyp_count, chunk, seed_key(seed), thr2, best_key);
+            hyp_count, chunk, seed_key(seed), thr2, best_key, pair_begin);
         if (int rc = finish_launch()) return rc;
     }
     return SKS_OK;
+}
+
+int sks_cuda_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
+                            const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,
+                            uint32_t hyp_count, uint64_t seed, float thr2,
+                            unsigned long long* best_key, void* stream)
+{
+    return sks_cuda_ransac_aca_shard_f32(corr, 0, n_pairs, n_pts, samples, hyp_stride, hyp_begin, hyp_count,
+                                         seed, thr2, best_key, stream);
 }
 
 int sks_cuda_ransac_finalize_f32(const float* corr, int64_t n_pairs, int32_t n_pts,
@@ -448,6 +458,17 @@ int sks_cuda_ransac_finalize_f32(const float* corr, int64_t n_pairs, int32_t n_p
                                  float thr2, const unsigned long long* best_key, float* H_best,
                                  uint32_t* inlier_count, uint8_t* inlier_mask, void* stream)
 {
+    return sks_cuda_ransac_finalize_shard_f32(corr, 0, n_pairs, n_pts, samples, hyp_stride, seed, thr2,
+                                              best_key, H_best, inlier_count, inlier_mask, stream);
+}
+
+int sks_cuda_ransac_finalize_shard_f32(const float* corr, int64_t pair_begin, int64_t n_pairs,
+                                       int32_t n_pts, const uint32_t* samples, uint32_t hyp_stride,
+                                       uint64_t seed, float thr2, const unsigned long long* best_key,
+                                       float* H_best, uint32_t* inlier_count, uint8_t* inlier_mask,
+                                       void* stream)
+{
+    if (pair_begin < 0) return SKS_ERR_INVALID_ARG;
     if (corr == nullptr || best_key == nullptr || H_best == nullptr || n_pairs < 0 || n_pts <= 0)
         return SKS_ERR_INVALID_ARG;
     if (!aligned16(corr) || (samples && !aligned16(samples))) return SKS_ERR_UNALIGNED;
@@ -456,7 +477,7 @@ int sks_cuda_ransac_finalize_f32(const float* corr, int64_t n_pairs, int32_t n_p
     if (n_pairs == 0) return SKS_OK;
     k_ransac_finalize<<<(unsigned)n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(corr), n_pts, samples, hyp_stride, seed_key(seed), thr2,
-        best_key, H_best, inlier_count, inlier_mask);
+        best_key, H_best, inlier_count, inlier_mask, pair_begin);
     return finish_launch();
 }
 

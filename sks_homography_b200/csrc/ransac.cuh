@@ -61,8 +61,11 @@ namespace sksb {
 
 constexpr int kRansacMaxTilePts = 8192;    // 128 KiB of shared memory at most
 
-__device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, uint32_t hyp,
-                                              const uint32_t* __restrict__ samples,
+// pair: index into this call's arrays; pair_id_base + pair: the pair's global id, which keys
+// the counter RNG (so a rank that holds only a shard of the pairs draws the same samples
+// as a rank that holds them all)
+__device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, int64_t pair_id_base,
+                                              uint32_t hyp, const uint32_t* __restrict__ samples,
                                               uint32_t hyp_stride, uint32_t n_pts, uint32_t (&idx)[4])
 {
     if (samples != nullptr) {
@@ -70,7 +73,7 @@ __device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, uint32
                               ((size_t)pair * hyp_stride + hyp));
         idx[0] = v.x; idx[1] = v.y; idx[2] = v.z; idx[3] = v.w;
     } else {
-        const uint64_t ctr = ((uint64_t)pair << 32) | (uint64_t)hyp;
+        const uint64_t ctr = ((uint64_t)(pair + pair_id_base) << 32) | (uint64_t)hyp;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             idx[k] = (uint32_t)(rng_u64(key, ctr, k) >> 32) % n_pts;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kRansacThreads)
 k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, int32_t tile_pts,
              const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
              uint32_t hyp_count, uint32_t chunk_size, uint64_t key, float thr2,
-             unsigned long long* __restrict__ best_key)
+             unsigned long long* __restrict__ best_key, int64_t pair_id_base)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float4* tile = reinterpret_cast<float4*>(smem);
@@ -251,7 +254,7 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
             live[j] = local < c_hi;
             hyp[j] = hyp_begin + (live[j] ? local : c_lo);
             uint32_t idx[4];
-            ransac_sample(key, pair, hyp[j], samples, hyp_stride, (uint32_t)n_pts, idx);
+            ransac_sample(key, pair, pair_id_base, hyp[j], samples, hyp_stride, (uint32_t)n_pts, idx);
             ransac_hypothesis(corr_pair, idx, h[j]);
             ransac_scale_h(h[j], it);
             cnt[j] = 0;
@@ -402,7 +405,7 @@ k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
                   const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint64_t key,
                   float thr2, const unsigned long long* __restrict__ best_key,
                   float* __restrict__ H_best, uint32_t* __restrict__ inlier_count,
-                  uint8_t* __restrict__ inlier_mask)
+                  uint8_t* __restrict__ inlier_mask, int64_t pair_id_base)
 {
     __shared__ float hs[9];
     __shared__ uint32_t total;
@@ -412,7 +415,7 @@ k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
         const uint32_t hyp = 0xFFFFFFFFu - (uint32_t)(best_key[pair] & 0xFFFFFFFFull);
         uint32_t idx[4];
         float h[9];
-        ransac_sample(key, pair, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
+        ransac_sample(key, pair, pair_id_base, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
         ransac_hypothesis(corr_pair, idx, h);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {

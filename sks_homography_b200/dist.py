@@ -160,3 +160,17 @@ def ransac_aca(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     H, cnt, mask = api.ransac_finalize(corr, n_hyp, seed, thr2, keys, samples, want_mask)
     _, hyp = api.decode_keys(keys)
     return H, cnt, hyp, mask
+
+
+def ransac_aca_pairs(corr_shard: torch.Tensor, pair_begin: int, n_hyp: int, seed: int, thr2: float,
+                     samples: torch.Tensor | None = None, want_mask: bool = False):
+    """Pair-sharded fused ACA-RANSAC (SURVEY.md 8(e) variant B): this rank owns image pairs
+    [pair_begin, pair_begin + P_local) and scores ALL hypothesis ids of them; no collective.
+    `pair_begin` keys the sampler, so the result equals rows [pair_begin, ...) of an unsharded run.
+    Returns (H_best [P_local,9], inlier_count, hyp_id, mask)."""
+    from . import api
+    keys = api.ransac_keys(corr_shard, n_hyp, seed, thr2, samples, pair_begin=pair_begin)
+    H, cnt, mask = api.ransac_finalize(corr_shard, n_hyp, seed, thr2, keys, samples, want_mask,
+                                       pair_begin=pair_begin)
+    _, hyp = api.decode_keys(keys)
+    return H, cnt, hyp, mask

@@ -41,6 +41,10 @@ def _worker(rank, world, port, out_dir):
         kt = torch.from_numpy(keys.view(np.int64).copy())
         sd.merge_keys(kt)
         np.save(os.path.join(out_dir, f"keys_{rank}.npy"), kt.numpy())
+        # --- RANSAC variant B: image pairs sharded, no collective; the global pair id keys the sampler
+        pb, pc = sd.shard_range(corr.shape[0])
+        kp = o.ransac(corr[pb:pb + pc], n_hyp, seed=17, thr2=4.0, pair_begin=pb)
+        np.save(os.path.join(out_dir, f"pairkeys_{rank}.npy"), kp)
     finally:
         dist.destroy_process_group()
 
@@ -63,3 +67,5 @@ def test_two_rank_sharding_and_key_merge(tmp_path, oracle):
     assert np.array_equal(k0, k1)
     assert np.array_equal(k0.view(np.uint64), full)
     assert ((full >> np.uint64(32)) >= 60).all()
+    # pair shards: concatenated == unsharded, without any exchange
+    assert np.array_equal(np.concatenate([np.load(tmp_path / f"pairkeys_{r}.npy") for r in range(world)]), full)

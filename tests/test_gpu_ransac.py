@@ -162,3 +162,25 @@ def test_host_pointer_entry_point(api, oracle, cuda):
                                          for p in range(P)], dtype=np.uint32).view(np.int32))
     _, _, _, k2 = api.ransac_host(corr.pin_memory(), n_hyp, seed=0, thr2=2.25, samples=samples)
     assert torch.equal(k2, keys)
+
+
+def test_pair_shards_equal_rows_of_the_unsharded_run(api, sks, oracle, cuda):
+    """Multi-GPU variant B (pairs sharded, no collective): a shard called with its global
+    pair_begin reproduces exactly its rows of the unsharded result (and of the oracle)."""
+    from sks_homography_b200 import dist as sd
+    P, n_pts, n_hyp = 7, 1500, 900
+    corr = api.synth_corr(P, n_pts, seed=5, device=cuda)
+    full = api.ransac_keys(corr, n_hyp, seed=3, thr2=2.25)
+    assert np.array_equal(u64(full), oracle.ransac(corr.cpu().numpy(), n_hyp, seed=3, thr2=2.25))
+    Hf, cf, _ = api.ransac_finalize(corr, n_hyp, 3, 2.25, full)
+    got_H, got_c, got_k = [], [], []
+    for r in range(3):
+        b, c = sks.shard_range(P, r, 3)
+        shard = api.synth_corr(c, n_pts, seed=5, device=cuda, pair_begin=b)     # a rank generates only its pairs
+        assert torch.equal(shard, corr[b:b + c])
+        H, cnt, hyp, _ = sd.ransac_aca_pairs(shard, b, n_hyp, 3, 2.25)
+        got_H.append(H); got_c.append(cnt); got_k.append(hyp)
+    assert torch.equal(torch.cat(got_H), Hf) and torch.equal(torch.cat(got_c), cf)
+    assert torch.equal(torch.cat(got_k), api.decode_keys(full)[1])
+    # without the global pair id the samples differ (the id keys the RNG)
+    assert not torch.equal(api.ransac_keys(corr[3:].contiguous(), n_hyp, 3, 2.25), full[3:])
