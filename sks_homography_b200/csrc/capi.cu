@@ -169,6 +169,18 @@ int launch_gather_solve(const T* pool, uint32_t pool_size, const uint32_t* rand4
     if (ld < n) return SKS_ERR_INVALID_ARG;
     constexpr int TILE = sizeof(T) == 4 ? 256 : 128;
     const int64_t grid = (n + TILE - 1) / TILE;
+    // SoA output with a pool that fits twice into an SM's shared memory: persistent CTAs gather
+    // from shared memory (variant 2 of sks_cuda_set_variant forces the L1 path for comparison)
+    const size_t pool_bytes = (size_t)pool_size * 4 * sizeof(T);
+    if (layout == SKS_LAYOUT_SOA && pool_bytes <= 96u * 1024 && n >= (int64_t)dev.sms * 2048 &&
+        g_variant.load() != 2) {
+        auto pk = k_gather_solve_pool<SOLVER, T>;
+        cudaError_t e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes);
+        if (e != cudaSuccess) return (int)e;
+        pk<<<(unsigned)(dev.sms * 2), 512, pool_bytes, static_cast<cudaStream_t>(stream)>>>(
+            pool, pool_size, rand4, seed_key(seed), H, degen, n, ld, (flags & SKS_FLAG_NORMALIZE) != 0);
+        return finish_launch();
+    }
     const bool wide = sizeof(T) == 8 && aligned32(pool) && g_wide.load() != 0;
     auto kern = wide ? k_gather_solve<SOLVER, T, TILE, true> : k_gather_solve<SOLVER, T, TILE, false>;
     kern<<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -355,6 +355,60 @@ k_gather_solve(const T* __restrict__ pool, uint32_t pool_size, const uint32_t* _
     }
 }
 
+// ------------------------------------------------------ k_gather_solve_pool
+// Same flow with the match pool held in SHARED memory by persistent CTAs (SoA output, the
+// reference GPU layout).  The L1 path above pays one L1 wavefront per lane for every random
+// 32-byte match (ncu: L1 71 % busy, the kernel's limiter); a 16-byte shared load serves eight
+// lanes per cycle when their banks differ, about three lanes with random indices.  Two
+// 512-thread CTAs per SM each copy the pool once (a few tens of KB against tens of MB of
+// output) and then walk tiles of 512 hypotheses without any barrier.
+template <int SOLVER, typename T>
+__global__ void __launch_bounds__(512)
+k_gather_solve_pool(const T* __restrict__ pool, uint32_t pool_size, const uint32_t* __restrict__ rand4,
+                    uint64_t key, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n,
+                    int64_t ld, bool normalize)
+{
+    extern __shared__ __align__(128) unsigned char pool_smem[];
+    Chunk16* sp = reinterpret_cast<Chunk16*>(pool_smem);
+    const int tid = threadIdx.x;
+    const uint32_t chunks = pool_size * (uint32_t)(4 * sizeof(T) / 16);
+    for (uint32_t c = tid; c < chunks; c += 512)
+        sp[c] = ldg_stream(reinterpret_cast<const Chunk16*>(pool) + c);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * 512 + tid; i < n; i += (int64_t)gridDim.x * 512) {
+        T s[8], t[8], h[9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t r;
+            if (rand4 != nullptr)
+                r = ldg_stream_u32(rand4 + (int64_t)k * n + i);
+            else {
+                uint64_t z = key ^ ((uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)k);
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+                r = (uint32_t)((z ^ (z >> 31)) >> 32);
+            }
+            const uint32_t e = r % pool_size;
+            if constexpr (sizeof(T) == 4) {
+                const Chunk16 m = lds16(sp + e);
+                s[2 * k] = ChunkTraits<T>::get(m, 0); s[2 * k + 1] = ChunkTraits<T>::get(m, 1);
+                t[2 * k] = ChunkTraits<T>::get(m, 2); t[2 * k + 1] = ChunkTraits<T>::get(m, 3);
+            } else {
+                const Chunk16 a = lds16(sp + 2 * e), b = lds16(sp + 2 * e + 1);
+                s[2 * k] = ChunkTraits<T>::get(a, 0); s[2 * k + 1] = ChunkTraits<T>::get(a, 1);
+                t[2 * k] = ChunkTraits<T>::get(b, 0); t[2 * k + 1] = ChunkTraits<T>::get(b, 1);
+            }
+        }
+        RectParams<T> none{};
+        solve_quad<SOLVER, T>(s, t, T(0), T(0), none, h, normalize);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            H[k * ld + i] = h[k];
+        if (degen != nullptr)
+            degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
+    }
+}
+
 // -------------------------------------------------------------- k_aos_ring
 template <int SOLVER, typename T, int TILE>
 struct RingLayout {

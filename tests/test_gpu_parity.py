@@ -438,6 +438,32 @@ def test_fused_gather_solve_equals_gather_then_solve(api, oracle, cuda, solver, 
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_gather_solve_shared_memory_pool(api, sks, oracle, cuda, dtype):
+    """Large SoA batches take the persistent kernel that keeps the match pool in shared memory;
+    it must agree with the L1-path kernel (forced by variant 2) and with gather + oracle."""
+    rng = np.random.default_rng(6)
+    pool = rng.uniform(7, 790, size=(2540, 4)).astype(dtype)
+    n = 700_001
+    d_pool = dev(pool, cuda)
+    rand4 = api.curand_mrg32k3a(4 * n, 11, cuda).view(4, n)
+    for r4 in (rand4, None):
+        H = api.gather_solve("aca", d_pool, n, seed=9, rand4=r4, normalize=False, layout="soa")
+        sks.c.sks_cuda_set_variant(2)
+        H_l1 = api.gather_solve("aca", d_pool, n, seed=9, rand4=r4, normalize=False, layout="soa")
+        sks.c.sks_cuda_set_variant(0)
+        assert torch.equal(H.view(torch.int32 if dtype == np.float32 else torch.int64),
+                           H_l1.view(torch.int32 if dtype == np.float32 else torch.int64))
+        src, tar = api.gather_samples(d_pool, n, seed=9, rand4=r4)
+        want = oracle.solve("aca", src[:50_000].cpu().numpy(), tar[:50_000].cpu().numpy(), normalize=False)
+        assert_same_bits(H[:, :50_000].cpu().numpy().T, want, "shared-memory pool gather")
+    big = dev(rng.uniform(7, 790, size=(20_000, 4)).astype(dtype), cuda)      # too large for shared memory
+    Hb = api.gather_solve("sks", big, n, seed=2, normalize=True, layout="soa")
+    src, tar = api.gather_samples(big, n, seed=2)
+    assert_same_bits(Hb[:, -30_000:].cpu().numpy().T,
+                     oracle.solve("sks", src[-30_000:].cpu().numpy(), tar[-30_000:].cpu().numpy()), "L1 fallback")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("solver", ["aca", "sks"])
 def test_extreme_magnitudes_overflow_and_denormals(api, oracle, cuda, solver, dtype):
     """Un-normalised entries are degree 7-9 polynomials of the coordinates (README.md:54):
