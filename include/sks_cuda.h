@@ -285,8 +285,10 @@ int64_t sks_cuda_launch_count(void);
 void sks_cuda_reset_launch_count(void);
 /* Kernel variant for the AoS streaming solvers: 0 = default (best measured, = 1),
  * 1 = direct vector loads + shared-memory transposed stores,
- * 2 = persistent TMA bulk-copy ring (cp.async.bulk + mbarrier).  A tuning knob
- * for bench.py sweeps, not a backend switch: every variant is sm_100a CUDA. */
+ * 2 = persistent TMA bulk-copy ring (cp.async.bulk + mbarrier); 2 also keeps the fused
+ * gather+solve entry points on their L1 gather path instead of the shared-memory-pool kernel.
+ * A tuning knob for bench.py sweeps and tests, not a backend switch: every variant is
+ * sm_100a CUDA. */
 int sks_cuda_set_variant(int variant);
 int sks_cuda_get_variant(void);
 /* Kernel tuning: small_tile bit 0 (ring kernel: 0 = 256 fp32 / 128 fp64 quadruples
