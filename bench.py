@@ -72,6 +72,7 @@ WORKLOADS = {
     # pivoting and fails on the axis-aligned source squares of dist 0
     "ge_f32": ("ge", "f32", 100, 26, 1),
     "ge_f64": ("ge", "f64", 200, 25, 1),
+    "gpt_f64": ("gpt", "f64", 200, 24, 1),     # GPT-LU, the arithmetic of cal_Homo_GPT (compute-bound)
 }
 
 
@@ -156,8 +157,8 @@ def run_reference(args):
     o = Oracle()
     kind = "reference"
     try:
-        if solver == "ge" and dt == "f64":
-            raise LookupError("the reference's C++ GE is fp32 only")
+        if (solver == "ge" and dt == "f64") or solver == "gpt":
+            raise LookupError("the reference's C++ GE is fp32 only; its GPT is OpenCV")
         ref = RefLib()
         threads = ref.hardware_threads()
         run = lambda s, t, out: ref.solve(solver, s, t, threads=threads, out=out)
@@ -384,8 +385,8 @@ def main():
         s_h, t_h = src[:S].cpu().numpy(), tar[:S].cpu().numpy()
         out = np.empty((S, 9), dtype=s_h.dtype)
         try:
-            if solver == "ge" and dt == "f64":
-                raise LookupError("the reference's C++ GE is fp32 only")
+            if (solver == "ge" and dt == "f64") or solver == "gpt":
+                raise LookupError("the reference's C++ GE is fp32 only; its GPT is OpenCV")
             ref = RefLib()
             threads, kind = ref.hardware_threads(), "reference"
             run = lambda: ref.solve(solver, s_h, t_h, threads=threads, out=out)
@@ -421,7 +422,7 @@ def main():
                 o3 = {"unavailable": str(e)[:100]}
         cpu = {"value": S / best, "unit": UNIT, "cores": threads, "kind": kind, "o3_fma_build": o3,
                "sample": f"first 2^{args.cpu_log2n} quadruples of the workload, best of 5 passes, "
-                         f"{'MOD/GE.cpp' if solver == 'ge' else 'MOD/ACA_SKS.cpp'} g++ -O2 -ffp-contract=off"
+                         f"{'MOD/GE.cpp' if solver == 'ge' else 'GPU.cu:242-357' if solver == 'gpt' else 'MOD/ACA_SKS.cpp'} g++ -O2 -ffp-contract=off"
                          f"{'' if kind == 'reference' else ' (oracle port)'}, {threads} threads",
                "parity_gpu_vs_cpu": parity}
 
@@ -484,7 +485,9 @@ def reference_gpu_kernels(api, dev):
         src, tar = api.synth_quads(n, 11, 1, torch.float64, dev, layout="soa")
         H = torch.empty((9, n), dtype=torch.float64, device=dev)
         st = torch.cuda.current_stream().cuda_stream
-        for solver in ("aca", "sks", "ge"):
+        for solver in ("aca", "sks", "ge", "gpt"):
+            if solver == "gpt" and log2n > 20:
+                continue                      # compute-bound: the Table-8 row is enough
             t_ref = _event_ms(lambda: ref.run(solver, src.data_ptr(), tar.data_ptr(), H.data_ptr(), n, st), 20)
             t_our = _event_ms(lambda: api.solve(solver, src, tar, result=H, normalize=False, layout="soa"), 20)
             out["rows"].append({"solver": solver, "n": n, "reference_us": 1e3 * t_ref, "ours_us": 1e3 * t_our,

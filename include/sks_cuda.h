@@ -85,6 +85,12 @@ int sks_cuda_ge_f32(const float *src, const float *tar, float *H, int64_t n, int
 int sks_cuda_ge_f64(const double *src, const double *tar, double *H, int64_t n, int layout,
                     int64_t ld, int flags, uint8_t *degenerate, void *stream);
 
+/* Second competitor, fp64 only: GPT-LU, the 8x8 DLT system by LU with partial pivoting in the
+ * arithmetic of cal_Homo_GPT            GPU.cu:242-357 (bit-equal to that kernel built with
+ * -fmad=false; its CPU form MOD/GPT.cpp is cv::getPerspectiveTransform, i.e. OpenCV). */
+int sks_cuda_gpt_f64(const double *src, const double *tar, double *H, int64_t n, int layout,
+                     int64_t ld, int flags, uint8_t *degenerate, void *stream);
+
 /* replaces ACA_rect(TargetPts, M_x, M_y, width, ratio_rec)  ML/ACA_rect.m:22-38
  *          TensorACA_rect(bs, src, tar, scale, div)         PY.py:286-309
  * tar holds the 4 target corners TL,TR,BL,BR (8 values per quadruple, the

@@ -199,7 +199,7 @@ class RefGpuLib:
         if not os.path.exists(so):
             raise FileNotFoundError(so)
         self.lib = C.CDLL(so)
-        for name in ("refgpu_aca_f64", "refgpu_sks_f64", "refgpu_ge_f64"):
+        for name in ("refgpu_aca_f64", "refgpu_sks_f64", "refgpu_ge_f64", "refgpu_gpt_f64"):
             fn = getattr(self.lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

@@ -1,6 +1,6 @@
 // TEST / BENCH INFRASTRUCTURE ONLY -- same-box GPU comparator.
 // Wraps the reference's own CUDA kernels cal_Homo_ACA / cal_Homo_SKS
-// ("GPU_Runtime Test.cu":81-240) and cal_Homo_GE (:359-507), which oracle/Makefile
+// ("GPU_Runtime Test.cu":81-240), cal_Homo_GE (:359-507) and cal_Homo_GPT (:242-357), which oracle/Makefile
 // extracts AT BUILD TIME
 // into the git-ignored oracle/_ref/ref_gpu_kernels.inc (nothing of the reference
 // is stored in this repository), and launches them exactly as the reference's
@@ -36,6 +36,14 @@ int refgpu_ge_f64(double* d_src, double* d_tar, double* d_H, int n, void* stream
     dim3 block = 32;                       // GPU.cu:1286-1287
     dim3 grid = (n + block.x - 1) / block.x;
     cal_Homo_GE<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_tar, d_H, n);
+    return (int)cudaGetLastError();
+}
+
+int refgpu_gpt_f64(double* d_src, double* d_tar, double* d_H, int n, void* stream)
+{
+    dim3 block = 32;
+    dim3 grid = (n + block.x - 1) / block.x;
+    cal_Homo_GPT<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_tar, d_H, n);
     return (int)cudaGetLastError();
 }
 

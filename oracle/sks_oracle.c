@@ -19,6 +19,9 @@
  *     fp64 is the same type-generic body (the reference's only fp64 GE is its
  *     FMA-contracted CUDA kernel GPU.cu:359-507; recompiled with -fmad=false into
  *     oracle/_ref/libsks_refgpu.so it is bit-compared on the GPU box).
+ *   GPT-LU (competitor, fp64): the arithmetic of the reference's CUDA kernel cal_Homo_GPT
+ *     (GPU.cu:242-357); pinned on the GPU box against that kernel compiled with -fmad=false.
+ *     (Its CPU form calls OpenCV's getPerspectiveTransform, which is outside the reference tree.)
  *   RANSAC scoring: PARITY UNPINNED -- the reference has no inlier test or model
  *     selection (only the sampler precedent GPU.cu:52-78).  Hypotheses are the
  *     pinned ACA; the scoring rule below is this project's own definition.
@@ -59,6 +62,8 @@ DEF_BATCH(oracle_sks_f32, float, oracle_sks_one_f32)
 DEF_BATCH(oracle_sks_f64, double, oracle_sks_one_f64)
 DEF_BATCH(oracle_ge_f32, float, oracle_ge_one_f32)
 DEF_BATCH(oracle_ge_f64, double, oracle_ge_one_f64)
+DEF_BATCH(oracle_gpt_f32, float, oracle_gpt_one_f32)
+DEF_BATCH(oracle_gpt_f64, double, oracle_gpt_one_f64)
 
 /* M == NULL: one shared rectangle corner (mx,my); else per-sample M[n][2]
  * (PyTorch Codes/Modules_Runtime_Test.py:302 reads M per sample while

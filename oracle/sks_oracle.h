@@ -28,6 +28,10 @@ void oracle_aca_f32(const float *src, const float *tar, float *H, int64_t n, int
 void oracle_aca_f64(const double *src, const double *tar, double *H, int64_t n, int normalize);
 void oracle_sks_f32(const float *src, const float *tar, float *H, int64_t n, int normalize);
 void oracle_sks_f64(const double *src, const double *tar, double *H, int64_t n, int normalize);
+void oracle_gpt_one_f32(const float *s, const float *t, float *h, int normalize);
+void oracle_gpt_one_f64(const double *s, const double *t, double *h, int normalize);
+void oracle_gpt_f32(const float *src, const float *tar, float *H, int64_t n, int normalize);
+void oracle_gpt_f64(const double *src, const double *tar, double *H, int64_t n, int normalize);
 void oracle_ge_f32(const float *src, const float *tar, float *H, int64_t n, int normalize);
 void oracle_ge_f64(const double *src, const double *tar, double *H, int64_t n, int normalize);
 void oracle_aca_rect_f32(const float *tar, const float *M, float mx, float my, float width,

@@ -47,6 +47,7 @@ _SIGS = {
     "sks_cuda_sks_f64": (_int, _GENERAL),
     "sks_cuda_ge_f32": (_int, _GENERAL),
     "sks_cuda_ge_f64": (_int, _GENERAL),
+    "sks_cuda_gpt_f64": (_int, _GENERAL),
     "sks_cuda_aca_rect_f32": (_int, [_vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "sks_cuda_aca_rect_f64": (_int, [_vp, _vp, _f64, _f64, _f64, _f64, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "sks_cuda_aca_rect_planar_f32": (_int, [_vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _int, _vp, _vp]),

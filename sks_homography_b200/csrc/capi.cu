@@ -283,6 +283,7 @@ SKS_DEFINE_GENERAL(sks_cuda_sks_f32, SOLVER_SKS, float)
 SKS_DEFINE_GENERAL(sks_cuda_sks_f64, SOLVER_SKS, double)
 SKS_DEFINE_GENERAL(sks_cuda_ge_f32, SOLVER_GE, float)
 SKS_DEFINE_GENERAL(sks_cuda_ge_f64, SOLVER_GE, double)
+SKS_DEFINE_GENERAL(sks_cuda_gpt_f64, SOLVER_GPT, double)
 
 #define SKS_DEFINE_RECT(NAME, T)                                                                \
     int NAME(const T* tar, const T* M, T mx, T my, T width, T ratio, T* H, int64_t n,           \

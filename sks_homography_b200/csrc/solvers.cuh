@@ -13,6 +13,7 @@
 //                     TensorACA_rect                PY.py:296-302
 //   ge_solve       <- cv::runKernel_GE (competitor) MOD/GE.cpp:44-188
 //                     cal_Homo_GE (fp64)            GPU.cu:359-507
+//   gpt_solve      <- cal_Homo_GPT (competitor)     GPU.cu:242-357
 #pragma once
 #include "strict.cuh"
 
@@ -333,6 +334,86 @@ __device__ __forceinline__ void ge_solve(const T (&s)[8], const T (&t)[8], T (&h
     h[0] = B[2][0].v; h[1] = B[2][1].v; h[2] = B[2][2].v;
     h[3] = B[2][4].v; h[4] = B[2][5].v; h[5] = B[2][6].v;
     h[6] = B[2][7].v; h[7] = B[2][3].v; h[8] = T(1);
+}
+
+// ---------------------------------------------------------------------- GPT
+// GPT-LU, the other competitor the paper times on the GPU: the 8x8 DLT system A h = b
+// (h33 = 1) by LU with partial pivoting, in the arithmetic of the reference's kernel
+// cal_Homo_GPT (GPU.cu:242-357).  The reference keeps A in a 64-double local array and
+// indexes it dynamically; here every index is a compile-time constant after unrolling, so A
+// and b live in registers and the data-dependent row swap is a chain of predicated
+// exchanges with the candidate rows below the diagonal.
+template <typename T>
+__device__ __forceinline__ void gpt_solve(const T (&s)[8], const T (&t)[8], T (&h)[9])
+{
+    using S = Strict<T>;
+    S A[8][8], b[8];
+    const S zero(T(0)), one(T(1));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const S x(s[2 * i]), y(s[2 * i + 1]), X(t[2 * i]), Y(t[2 * i + 1]);
+        A[i][0] = x; A[i][1] = y; A[i][2] = one; A[i][3] = zero; A[i][4] = zero; A[i][5] = zero;
+        A[i][6] = (-x) * X; A[i][7] = (-y) * X;
+        A[i + 4][0] = zero; A[i + 4][1] = zero; A[i + 4][2] = zero; A[i + 4][3] = x; A[i + 4][4] = y;
+        A[i + 4][5] = one; A[i + 4][6] = (-x) * Y; A[i + 4][7] = (-y) * Y;
+        b[i] = X;
+        b[i + 4] = Y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        // partial pivoting: first row with the largest |A[r][i]|, r >= i (NaN never wins)
+        int piv = i;
+        T best = fabs(A[i][i].v);
+#pragma unroll
+        for (int r = i + 1; r < 8; ++r) {
+            const T v = fabs(A[r][i].v);
+            if (best < v) {
+                piv = r;
+                best = v;
+            }
+        }
+#pragma unroll
+        for (int r = i + 1; r < 8; ++r) {          // branch-free exchange with the chosen row
+            const bool sw = (r == piv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const T ai = A[i][j].v, ar = A[r][j].v;
+                A[i][j] = S(sw ? ar : ai);
+                A[r][j] = S(sw ? ai : ar);
+            }
+            const T bi = b[i].v, br = b[r].v;
+            b[i] = S(sw ? br : bi);
+            b[r] = S(sw ? bi : br);
+        }
+#pragma unroll
+        for (int j = i + 1; j < 8; ++j)
+            A[i][j] = A[i][j] / A[i][i];
+#pragma unroll
+        for (int r = i + 1; r < 8; ++r)
+#pragma unroll
+            for (int j = i + 1; j < 8; ++j)
+                A[r][j] = A[r][j] - A[r][i] * A[i][j];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {          // L y = b
+        S acc = b[k];
+#pragma unroll
+        for (int j = 0; j < k; ++j)
+            acc = acc - A[k][j] * b[j];
+        b[k] = acc / A[k][k];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; --k) {         // U x = y (unit diagonal)
+        S acc = b[k];
+#pragma unroll
+        for (int j = 7; j > k; --j)
+            acc = acc - A[k][j] * b[j];
+        b[k] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        h[k] = b[k].v;
+    h[8] = T(1);
 }
 
 }  // namespace sksb

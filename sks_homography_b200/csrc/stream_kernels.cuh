@@ -26,7 +26,7 @@
 
 namespace sksb {
 
-enum { SOLVER_ACA = 0, SOLVER_SKS = 1, SOLVER_RECT = 2, SOLVER_GE = 3 };
+enum { SOLVER_ACA = 0, SOLVER_SKS = 1, SOLVER_RECT = 2, SOLVER_GE = 3, SOLVER_GPT = 4 };
 
 template <typename T>
 struct RectParams {
@@ -43,6 +43,8 @@ __device__ __forceinline__ void solve_quad(const T (&s)[8], const T (&t)[8], T m
         sks_solve<T>(s, t, h, normalize);
     else if constexpr (SOLVER == SOLVER_GE)
         ge_solve<T>(s, t, h);          // h33 = 1 by construction, with or without `normalize`
+    else if constexpr (SOLVER == SOLVER_GPT)
+        gpt_solve<T>(s, t, h);
     else
         aca_rect_solve<T>(t, mx, my, rp.width, rp.ratio, h, normalize);
 }

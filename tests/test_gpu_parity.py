@@ -104,10 +104,31 @@ def test_ge_competitor_bit_exact(api, sks, oracle, golden, cuda, dtype, variant)
         assert_same_bits(H.numpy(), oracle.solve("ge", s, t), "ge host path")
 
 
-@pytest.mark.parametrize("solver", ["aca", "sks", "ge"])
+@pytest.mark.parametrize("variant", ["direct", "ring"])
+def test_gpt_lu_competitor_bit_exact(api, sks, oracle, cuda, variant):
+    """GPT-LU (fp64, the arithmetic of cal_Homo_GPT): AoS / SoA against the CPU restatement,
+    including quadruples whose pivot search has to swap rows and exact degenerate ones."""
+    set_variant(sks, variant)
+    for n, dist in (((1 << 17) + 5, 1), (4099, 0), (2, 1), (0, 1)):
+        s, t = oracle.synth_quads(23, n, 31 + dist, dist, np.float64)
+        want = oracle.solve("gpt", s, t).reshape(n, 9)
+        H = api.solve("gpt", dev(s, cuda).view(n, 8), dev(t, cuda).view(n, 8))
+        assert_same_bits(H.cpu().numpy(), want, f"gpt aos n={n}")
+        if n:
+            Hs = api.solve("gpt", dev(s.T, cuda), dev(t.T, cuda), normalize=False, layout="soa")
+            assert_same_bits(Hs.cpu().numpy().T, want, f"gpt soa n={n}")
+    deg = np.array([[0, 0, 1, 0, 2, 0, 1, 1], [0, 0, 4, 0, 0, 3, 5, 4], [2, 2, 2, 2, 2, 2, 2, 2]], np.float64)
+    H = api.solve("gpt", dev(deg, cuda), dev(deg[::-1].copy(), cuda))
+    assert_same_bits(H.cpu().numpy(), oracle.solve("gpt", deg, deg[::-1].copy()), "gpt degenerate")
+    s, t = oracle.synth_quads(0, 20_000, 7, 1, np.float64)
+    g = api.solve("gpt", dev(s, cuda), dev(t, cuda)).cpu().numpy()
+    assert reproject_error(g, s, t).max() < 1e-6
+
+
+@pytest.mark.parametrize("solver", ["aca", "sks", "ge", "gpt"])
 def test_soa_fp64_equals_reference_cuda_kernels_without_fma(api, cuda, solver):
     """GPU-side pin of rows a5/a6 (and fp64 GE): the reference's own kernels
-    cal_Homo_ACA / cal_Homo_SKS / cal_Homo_GE (GPU.cu:81-240, :359-507) compiled with
+    cal_Homo_ACA / cal_Homo_SKS / cal_Homo_GE / cal_Homo_GPT (GPU.cu:81-240, :359-507, :242-357) compiled with
     -fmad=false round every operation on its own, like the reference's C++; launched as
     the reference launches them (SoA fp64, block 32, un-normalised) they must produce
     the same bits as our SoA kernels on the same device buffers."""
