@@ -110,6 +110,16 @@ def runKernel_GE(src, tar, result=None, **kw):
     return solve("ge", src, tar, result, **kw)
 
 
+def runKernel_GPT(src, tar, result=None, **kw):
+    """Competitor GPT-LU in the arithmetic of the reference's CUDA kernel cal_Homo_GPT
+    (GPU.cu:242-357): float64 device tensors only (the reference's CPU form is OpenCV's
+    getPerspectiveTransform and is not part of this library)."""
+    _check_pair(src, tar, torch.float64)
+    if not src.is_cuda:
+        raise ValueError("runKernel_GPT takes device tensors")
+    return solve("gpt", src, tar, result, **kw)
+
+
 def aca_rect(tar: torch.Tensor, width: float, ratio: float, M_x: float = 0.0, M_y: float = 0.0,
              M: torch.Tensor | None = None, result: torch.Tensor | None = None,
              normalize: bool = True, layout: str = "aos",
