@@ -52,7 +52,7 @@ print(f"{'N':>9s} | {'solver':6s} | {'reference us':>12s} | {'ours us':>9s} | {'
 for n in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
     src, tar = api.synth_quads(n, 11, 1, torch.float64, dev, layout="soa")
     H = torch.empty((9, n), dtype=torch.float64, device=dev)
-    for solver in ("aca", "sks"):
+    for solver in ("aca", "sks", "ge", "gpt"):      # the paper's Table 8 also times RHO-GE and GPT-LU
         st = lambda: torch.cuda.current_stream().cuda_stream
         t_ref = time_us(lambda: ref.run(solver, src.data_ptr(), tar.data_ptr(), H.data_ptr(), n, st()))
         ours = lambda: api.solve(solver, src, tar, result=H, normalize=False, layout="soa")
