@@ -86,3 +86,21 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "libsks_oracle" not in text and "libsks_ref" not in text, f
+
+
+def test_only_tests_bench_and_smoke_touch_the_oracle():
+    """oracle/ is the checker: besides tests/, bench.py (cpu_baseline / reference arm) and
+    __graft_entry__ (build + smoke), no Python file of the repository imports it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for d, _, files in os.walk(root):
+        rel = os.path.relpath(d, root)
+        if rel.split(os.sep)[0] in ("tests", "oracle", ".git", "gpurun_out", "baseline", "sks-homography_b200"):
+            continue
+        for f in files:
+            if f.endswith(".py") and not (rel == "." and f in ("bench.py", "__graft_entry__.py")):
+                text = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M):
+                    offenders.append(os.path.join(rel, f))
+    assert not offenders, offenders

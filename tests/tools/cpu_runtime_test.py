@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.oracle import Oracle, RefLib   # noqa: E402
 
 PAPER_US = {("aca", "f32"): 0.0145, ("aca", "f64"): 0.0171, ("sks", "f32"): 0.0252, ("sks", "f64"): 0.0256,
