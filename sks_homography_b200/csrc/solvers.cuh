@@ -359,6 +359,11 @@ __device__ __forceinline__ void gpt_solve(const T (&s)[8], const T (&t)[8], T (&
         b[i] = X;
         b[i + 4] = Y;
     }
+    // The forward substitution L y = b is carried along as a ninth column: the reference
+    // computes y_k = (((b_k - L_k0 y_0) - L_k1 y_1) - ...) / L_kk after the factorisation
+    // (GPU.cu:283-292); subtracting L_ri * y_i from b_r at step i performs the same operations
+    // in the same order, and a row's partial sum travels with the row through later swaps.
+    // Columns left of the diagonal are then dead, so each swap only touches columns >= i.
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         // partial pivoting: first row with the largest |A[r][i]|, r >= i (NaN never wins)
@@ -376,31 +381,27 @@ __device__ __forceinline__ void gpt_solve(const T (&s)[8], const T (&t)[8], T (&
         for (int r = i + 1; r < 8; ++r) {          // branch-free exchange with the chosen row
             const bool sw = (r == piv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const T ai = A[i][j].v, ar = A[r][j].v;
-                A[i][j] = S(sw ? ar : ai);
-                A[r][j] = S(sw ? ai : ar);
-            }
+            for (int j = 0; j < 8; ++j)
+                if (j >= i) {                      // constant after unrolling: dead columns drop out
+                    const T ai = A[i][j].v, ar = A[r][j].v;
+                    A[i][j] = S(sw ? ar : ai);
+                    A[r][j] = S(sw ? ai : ar);
+                }
             const T bi = b[i].v, br = b[r].v;
             b[i] = S(sw ? br : bi);
             b[r] = S(sw ? bi : br);
         }
+        b[i] = b[i] / A[i][i];
 #pragma unroll
         for (int j = i + 1; j < 8; ++j)
             A[i][j] = A[i][j] / A[i][i];
 #pragma unroll
-        for (int r = i + 1; r < 8; ++r)
+        for (int r = i + 1; r < 8; ++r) {
 #pragma unroll
             for (int j = i + 1; j < 8; ++j)
                 A[r][j] = A[r][j] - A[r][i] * A[i][j];
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {          // L y = b
-        S acc = b[k];
-#pragma unroll
-        for (int j = 0; j < k; ++j)
-            acc = acc - A[k][j] * b[j];
-        b[k] = acc / A[k][k];
+            b[r] = b[r] - A[r][i] * b[i];
+        }
     }
 #pragma unroll
     for (int k = 6; k >= 0; --k) {         // U x = y (unit diagonal)
