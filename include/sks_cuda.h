@@ -231,6 +231,15 @@ int sks_cuda_ransac_finalize_f32(const float *corr, int64_t n_pairs, int32_t n_p
                                  float thr2, const unsigned long long *best_key, float *H_best,
                                  uint32_t *inlier_count, uint8_t *inlier_mask, void *stream);
 
+/* Post-RANSAC re-estimation hook (new; nothing like it in the reference): least-squares
+ * homography of every pair from ALL matches flagged in inlier_mask [n_pairs][n_pts] (as written
+ * by sks_cuda_ransac_finalize_f32): Hartley-normalised DLT normal equations accumulated and
+ * solved in fp64, one warp per pair.  H_out [n_pairs][9] is h33-normalised; pairs with fewer
+ * than 4 inliers or a non-finite solution keep H_in (n_used = 0 for them). */
+int sks_cuda_ransac_refit_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                              const uint8_t *inlier_mask, const float *H_in, float *H_out,
+                              uint32_t *n_used, void *stream);
+
 /* ---- consumer after the path: sampling grids for image warping ------------- */
 /* New (the reference only remarks that warping does not need the normalisation,
  * ML/ACA_rect.m:33-35).  grid_xy[n][gh][gw][2] = (u, v) * (1/w) with (u,v,w) =

@@ -95,6 +95,17 @@ class Oracle:
         fn(_p(src), _p(tar), C.c_int64(begin), C.c_int64(count), C.c_uint64(seed), C.c_int(dist))
         return src, tar
 
+    def ransac_refit(self, corr, mask, H_in):
+        corr = _c(corr, np.float32)
+        P, n_pts, _ = corr.shape
+        mask = _c(mask, np.uint8).reshape(P, n_pts)
+        H_in = _c(H_in, np.float32).reshape(P, 9)
+        out = np.empty((P, 9), dtype=np.float32)
+        used = np.empty(P, dtype=np.uint32)
+        self.lib.oracle_ransac_refit_f32(_p(corr), C.c_int64(P), C.c_int32(n_pts), _p(mask), _p(H_in),
+                                         _p(out), _p(used))
+        return out, used
+
     def warp_grid(self, H, gw: int, gh: int, x0=0.0, y0=0.0, dx=1.0, dy=1.0) -> np.ndarray:
         H = _c(H, np.float32).reshape(-1, 9)
         out = np.empty((H.shape[0], gh, gw, 2), dtype=np.float32)

@@ -175,6 +175,109 @@ static inline double u01_f64(uint64_t r) { return (double)(r >> 11) * 0x1p-53; }
 DEF_SYNTH(oracle_synth_quads_f32, float, u01_f32)
 DEF_SYNTH(oracle_synth_quads_f64, double, u01_f64)
 
+/* ------------------------------------------------------- post-RANSAC refit */
+/* Our own definition (parity unpinned); mirrors csrc/refit.cuh operation for operation,
+ * including the reduction order: 32 "lanes" take matches lane, lane+32, ... in index order and
+ * are combined by the xor tree 16, 8, 4, 2, 1 (addition is commutative, so every lane of the
+ * device warp ends with these bits). */
+static double refit_tree(double v[32])
+{
+    for (int off = 16; off > 0; off >>= 1) {
+        double w[32];
+        for (int l = 0; l < 32; ++l)
+            w[l] = v[l] + v[l ^ off];
+        memcpy(v, w, sizeof w);
+    }
+    return v[0];
+}
+
+void oracle_ransac_refit_f32(const float *corr, int64_t n_pairs, int32_t n_pts, const uint8_t *mask,
+                             const float *H_in, float *H_out, uint32_t *n_used)
+{
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const float *c = corr + 4 * (size_t)n_pts * (size_t)p;
+        const uint8_t *m = mask + (size_t)n_pts * (size_t)p;
+        double l0[5][32];
+        memset(l0, 0, sizeof l0);
+        for (int l = 0; l < 32; ++l)
+            for (int i = l; i < n_pts; i += 32)
+                if (m[i]) {
+                    for (int k = 0; k < 4; ++k)
+                        l0[k][l] = l0[k][l] + (double)c[4 * i + k];
+                    l0[4][l] = l0[4][l] + 1.0;
+                }
+        const double sx = refit_tree(l0[0]), sy = refit_tree(l0[1]), sX = refit_tree(l0[2]),
+                     sY = refit_tree(l0[3]), cnt = refit_tree(l0[4]);
+        const double cx = sx / cnt, cy = sy / cnt, cX = sX / cnt, cY = sY / cnt;
+        double l1[2][32];
+        memset(l1, 0, sizeof l1);
+        for (int l = 0; l < 32; ++l)
+            for (int i = l; i < n_pts; i += 32)
+                if (m[i]) {
+                    const double ax = (double)c[4 * i] - cx, ay = (double)c[4 * i + 1] - cy;
+                    const double bx = (double)c[4 * i + 2] - cX, by = (double)c[4 * i + 3] - cY;
+                    l1[0][l] = l1[0][l] + sqrt(ax * ax + ay * ay);
+                    l1[1][l] = l1[1][l] + sqrt(bx * bx + by * by);
+                }
+        const double d1 = refit_tree(l1[0]), d2 = refit_tree(l1[1]);
+        const double r2 = 1.4142135623730951;
+        const double s1 = (r2 * cnt) / d1, s2 = (r2 * cnt) / d2;
+        static double N[36][32], g[8][32];      /* not re-entrant: test infrastructure */
+        memset(N, 0, sizeof N);
+        memset(g, 0, sizeof g);
+        for (int l = 0; l < 32; ++l)
+            for (int i = l; i < n_pts; i += 32)
+                if (m[i]) {
+                    const double u = ((double)c[4 * i] - cx) * s1, v = ((double)c[4 * i + 1] - cy) * s1;
+                    const double U = ((double)c[4 * i + 2] - cX) * s2, V = ((double)c[4 * i + 3] - cY) * s2;
+                    const double aX[8] = { u, v, 1.0, 0.0, 0.0, 0.0, -u * U, -v * U };
+                    const double aY[8] = { 0.0, 0.0, 0.0, u, v, 1.0, -u * V, -v * V };
+                    int k = 0;
+                    for (int a = 0; a < 8; ++a) {
+                        for (int b = a; b < 8; ++b, ++k)
+                            N[k][l] = N[k][l] + (aX[a] * aX[b] + aY[a] * aY[b]);
+                        g[a][l] = g[a][l] + (aX[a] * U + aY[a] * V);
+                    }
+                }
+        double A[8][8], b[8];
+        {
+            int k = 0;
+            for (int a = 0; a < 8; ++a) {
+                for (int bb = a; bb < 8; ++bb, ++k) {
+                    const double t = refit_tree(N[k]);
+                    A[a][bb] = t;
+                    A[bb][a] = t;
+                }
+                b[a] = refit_tree(g[a]);
+            }
+        }
+        oracle_lu8_solve_f64(A, b);
+        const double hn[9] = { b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.0 };
+        double M[9], Hd[9];
+        for (int r = 0; r < 3; ++r) {
+            M[3 * r] = hn[3 * r] * s1;
+            M[3 * r + 1] = hn[3 * r + 1] * s1;
+            M[3 * r + 2] = (hn[3 * r + 2] - M[3 * r] * cx) - M[3 * r + 1] * cy;
+        }
+        const double is2 = 1.0 / s2;
+        for (int k = 0; k < 3; ++k) {
+            Hd[k] = M[k] * is2 + cX * M[6 + k];
+            Hd[3 + k] = M[3 + k] * is2 + cY * M[6 + k];
+            Hd[6 + k] = M[6 + k];
+        }
+        int ok = cnt >= 4.0;
+        float out[9];
+        for (int k = 0; k < 9; ++k) {
+            out[k] = (float)(Hd[k] / Hd[8]);
+            ok = ok && isfinite(out[k]);
+        }
+        for (int k = 0; k < 9; ++k)
+            H_out[9 * p + k] = ok ? out[k] : H_in[9 * p + k];
+        if (n_used)
+            n_used[p] = ok ? (uint32_t)cnt : 0u;
+    }
+}
+
 /* ------------------------------------------------------------ warp grid */
 /* Our own definition (parity unpinned: the reference only remarks that warping
  * needs no normalisation, ML/ACA_rect.m:33-35); mirrors csrc/warp.cuh. */

@@ -48,6 +48,12 @@ void oracle_synth_quads_f32(float *src, float *tar, int64_t begin, int64_t count
 void oracle_synth_quads_f64(double *src, double *tar, int64_t begin, int64_t count,
                             uint64_t seed, int dist);
 
+/* post-RANSAC least-squares refit on the inlier mask (consumer after the path; our definition) */
+void oracle_lu8_solve_f32(float A[8][8], float b[8]);
+void oracle_lu8_solve_f64(double A[8][8], double b[8]);
+void oracle_ransac_refit_f32(const float *corr, int64_t n_pairs, int32_t n_pts, const uint8_t *mask,
+                             const float *H_in, float *H_out, uint32_t *n_used);
+
 /* sampling grid of a homography (consumer after the path; our definition) */
 void oracle_warp_grid_f32(const float *H, int64_t n, float x0, float y0, float dx, float dy,
                           int32_t gw, int32_t gh, float *out);

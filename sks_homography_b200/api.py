@@ -369,6 +369,21 @@ def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys
     return H, cnt, mask
 
 
+def ransac_refit(corr: torch.Tensor, mask: torch.Tensor, H: torch.Tensor):
+    """Least-squares re-estimation of every pair's homography from all matches flagged in
+    `mask` [P, n_pts] (uint8, as returned by ransac_finalize(..., want_mask=True)); pairs
+    without a usable solution keep `H`.  Returns (H_refit [P,9], n_used [P])."""
+    L = lib()
+    corr, mask, H = corr.contiguous(), mask.contiguous(), H.contiguous()
+    P, n_pts, _ = corr.shape
+    out = torch.empty((P, 9), dtype=torch.float32, device=corr.device)
+    used = torch.empty(P, dtype=torch.int32, device=corr.device)
+    with torch.cuda.device(corr.device):
+        L.check(L.c.sks_cuda_ransac_refit_f32(_ptr(corr), P, n_pts, _ptr(mask), _ptr(H), _ptr(out), _ptr(used),
+                                              _stream_ptr(corr)), "sks_cuda_ransac_refit_f32")
+    return out, used
+
+
 def decode_keys(keys: torch.Tensor):
     """packed key -> (inlier count, hypothesis id)"""
     count = keys >> 32

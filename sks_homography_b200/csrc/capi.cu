@@ -13,6 +13,7 @@
 #include "mrg32k3a.cuh"
 #include "peer.cuh"
 #include "ransac.cuh"
+#include "refit.cuh"
 #include "stream_kernels.cuh"
 #include "synth.cuh"
 #include "warp.cuh"
@@ -491,6 +492,21 @@ int sks_cuda_ransac_finalize_shard_f32(const float* corr, int64_t pair_begin, in
     k_ransac_finalize<<<(unsigned)n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(corr), n_pts, samples, hyp_stride, seed_key(seed), thr2,
         best_key, H_best, inlier_count, inlier_mask, pair_begin);
+    return finish_launch();
+}
+
+int sks_cuda_ransac_refit_f32(const float* corr, int64_t n_pairs, int32_t n_pts, const uint8_t* inlier_mask,
+                              const float* H_in, float* H_out, uint32_t* n_used, void* stream)
+{
+    if (corr == nullptr || inlier_mask == nullptr || H_in == nullptr || H_out == nullptr || n_pairs < 0 ||
+        n_pts <= 0)
+        return SKS_ERR_INVALID_ARG;
+    if (!aligned16(corr)) return SKS_ERR_UNALIGNED;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n_pairs == 0) return SKS_OK;
+    k_ransac_refit<<<(unsigned)((n_pairs + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(corr), n_pairs, n_pts, inlier_mask, H_in, H_out, n_used);
     return finish_launch();
 }
 

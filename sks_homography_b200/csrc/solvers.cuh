@@ -336,29 +336,12 @@ __device__ __forceinline__ void ge_solve(const T (&s)[8], const T (&t)[8], T (&h
     h[6] = B[2][7].v; h[7] = B[2][3].v; h[8] = T(1);
 }
 
-// ---------------------------------------------------------------------- GPT
-// GPT-LU, the other competitor the paper times on the GPU: the 8x8 DLT system A h = b
-// (h33 = 1) by LU with partial pivoting, in the arithmetic of the reference's kernel
-// cal_Homo_GPT (GPU.cu:242-357).  The reference keeps A in a 64-double local array and
-// indexes it dynamically; here every index is a compile-time constant after unrolling, so A
-// and b live in registers and the data-dependent row swap is a chain of predicated
-// exchanges with the candidate rows below the diagonal.
+// A x = b for an 8x8 system by LU with partial pivoting, in place; x is left in b.  The
+// operation order is that of the reference's cal_Homo_GPT (GPU.cu:242-292, :345-355).
 template <typename T>
-__device__ __forceinline__ void gpt_solve(const T (&s)[8], const T (&t)[8], T (&h)[9])
+__device__ __forceinline__ void lu8_solve(Strict<T> (&A)[8][8], Strict<T> (&b)[8])
 {
     using S = Strict<T>;
-    S A[8][8], b[8];
-    const S zero(T(0)), one(T(1));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const S x(s[2 * i]), y(s[2 * i + 1]), X(t[2 * i]), Y(t[2 * i + 1]);
-        A[i][0] = x; A[i][1] = y; A[i][2] = one; A[i][3] = zero; A[i][4] = zero; A[i][5] = zero;
-        A[i][6] = (-x) * X; A[i][7] = (-y) * X;
-        A[i + 4][0] = zero; A[i + 4][1] = zero; A[i + 4][2] = zero; A[i + 4][3] = x; A[i + 4][4] = y;
-        A[i + 4][5] = one; A[i + 4][6] = (-x) * Y; A[i + 4][7] = (-y) * Y;
-        b[i] = X;
-        b[i + 4] = Y;
-    }
     // The forward substitution L y = b is carried along as a ninth column: the reference
     // computes y_k = (((b_k - L_k0 y_0) - L_k1 y_1) - ...) / L_kk after the factorisation
     // (GPU.cu:283-292); subtracting L_ri * y_i from b_r at step i performs the same operations
@@ -411,6 +394,32 @@ __device__ __forceinline__ void gpt_solve(const T (&s)[8], const T (&t)[8], T (&
             acc = acc - A[k][j] * b[j];
         b[k] = acc;
     }
+}
+
+// ---------------------------------------------------------------------- GPT
+// GPT-LU, the other competitor the paper times on the GPU: the 8x8 DLT system A h = b
+// (h33 = 1) by LU with partial pivoting, in the arithmetic of the reference's kernel
+// cal_Homo_GPT (GPU.cu:242-357).  The reference keeps A in a 64-double local array and
+// indexes it dynamically; here every index is a compile-time constant after unrolling, so A
+// and b live in registers and the data-dependent row swap is a chain of predicated
+// exchanges with the candidate rows below the diagonal.
+template <typename T>
+__device__ __forceinline__ void gpt_solve(const T (&s)[8], const T (&t)[8], T (&h)[9])
+{
+    using S = Strict<T>;
+    S A[8][8], b[8];
+    const S zero(T(0)), one(T(1));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const S x(s[2 * i]), y(s[2 * i + 1]), X(t[2 * i]), Y(t[2 * i + 1]);
+        A[i][0] = x; A[i][1] = y; A[i][2] = one; A[i][3] = zero; A[i][4] = zero; A[i][5] = zero;
+        A[i][6] = (-x) * X; A[i][7] = (-y) * X;
+        A[i + 4][0] = zero; A[i + 4][1] = zero; A[i + 4][2] = zero; A[i + 4][3] = x; A[i + 4][4] = y;
+        A[i + 4][5] = one; A[i + 4][6] = (-x) * Y; A[i + 4][7] = (-y) * Y;
+        b[i] = X;
+        b[i + 4] = Y;
+    }
+    lu8_solve<T>(A, b);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         h[k] = b[k].v;

@@ -184,3 +184,34 @@ def test_pair_shards_equal_rows_of_the_unsharded_run(api, sks, oracle, cuda):
     assert torch.equal(torch.cat(got_k), api.decode_keys(full)[1])
     # without the global pair id the samples differ (the id keys the RNG)
     assert not torch.equal(api.ransac_keys(corr[3:].contiguous(), n_hyp, 3, 2.25), full[3:])
+
+
+def test_refit_on_inlier_mask(api, oracle, cuda):
+    """Post-RANSAC hook: least-squares refit of each winner on its inlier mask, bit-exact with the
+    CPU port (same lane partial sums, same shuffle-tree order, same LU), and at least as good."""
+    P, n_pts, n_hyp = 9, 3000, 2048
+    corr = api.synth_corr(P, n_pts, seed=12, device=cuda)
+    keys = api.ransac_keys(corr, n_hyp, seed=6, thr2=2.25)
+    H, cnt, mask = api.ransac_finalize(corr, n_hyp, 6, 2.25, keys, want_mask=True)
+    Hr, used = api.ransac_refit(corr, mask, H)
+    want, want_used = oracle.ransac_refit(corr.cpu().numpy(), mask.cpu().numpy(), H.cpu().numpy())
+    assert np.array_equal(Hr.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(used.cpu().numpy().astype(np.uint32), want_used)
+    assert torch.equal(used.long(), cnt.long())
+    c_np, m_np = corr.cpu().numpy().astype(np.float64), mask.cpu().numpy().astype(bool)
+
+    def rms(Hs):                                 # transfer error over each pair's mask, in pixels
+        out = []
+        for p in range(P):
+            x = c_np[p][m_np[p]]
+            q = np.concatenate([x[:, :2], np.ones((len(x), 1))], 1) @ Hs[p].astype(np.float64).reshape(3, 3).T
+            out.append(np.sqrt((((q[:, :2] / q[:, 2:]) - x[:, 2:]) ** 2).sum(1).mean()))
+        return np.array(out)
+    e_before, e_after = rms(H.cpu().numpy()), rms(Hr.cpu().numpy())
+    assert (e_after < e_before).all() and e_after.max() < 0.6     # noise is +-0.5 px uniform
+    after = sum(oracle.ransac_count(Hr[p].cpu().numpy(), corr[p].cpu().numpy(), 2.25) for p in range(P))
+    assert after >= 0.98 * int(cnt.sum())        # and it still explains the winner's inliers
+    mask[0] = 0
+    mask[0, :3] = 1                              # too few inliers: the 4-point winner is kept
+    Hk, uk = api.ransac_refit(corr, mask, H)
+    assert torch.equal(Hk[0], H[0]) and int(uk[0]) == 0

@@ -175,6 +175,31 @@ def test_curand_mrg32k3a_restatement_matches_library_output(oracle, golden):
     assert oracle.curand_mrg32k3a(0, 11).size == 0
 
 
+def test_refit_port_recovers_a_planted_model(oracle):
+    """Post-RANSAC least-squares refit (our definition): noisy inliers of a known homography."""
+    rng = np.random.default_rng(0)
+    P, n = 3, 600
+    Ht = np.array([[1.1, 0.05, 12], [-0.03, 0.95, -7], [1e-4, -2e-4, 1]])
+    x = rng.uniform(10, 600, (P, n, 2))
+    q = np.concatenate([x, np.ones((P, n, 1))], -1) @ Ht.T
+    X = q[..., :2] / q[..., 2:] + rng.normal(0, 0.3, (P, n, 2))
+    corr = np.concatenate([x, X], -1).astype(np.float32)
+    mask = np.ones((P, n), np.uint8)
+    mask[:, ::7] = 0
+    corr[:, ::7, 2:] += 50                                   # gross outliers, masked out
+    H0 = np.tile(np.eye(3, dtype=np.float32).ravel(), (P, 1))
+    H, used = oracle.ransac_refit(corr, mask, H0)
+    assert (used == mask.sum(1)).all()
+    assert reproject_error(H, np.tile([10, 10, 600, 10, 10, 600, 600, 600], (P, 1)),
+                           np.tile((np.array([[10, 10, 1], [600, 10, 1], [10, 600, 1], [600, 600, 1]]) @ Ht.T
+                                    / (np.array([[10, 10, 1], [600, 10, 1], [10, 600, 1], [600, 600, 1]]) @ Ht.T)[:, 2:]
+                                    )[:, :2].reshape(8), (P, 1))).max() < 0.2
+    few = np.zeros_like(mask)
+    few[:, :3] = 1                                           # fewer than 4 inliers: keep the input model
+    H2, used2 = oracle.ransac_refit(corr, few, H0)
+    assert (used2 == 0).all() and np.array_equal(H2, H0)
+
+
 def test_warp_grid_port_maps_rectangle_corners_to_targets(oracle):
     _, t = oracle.synth_quads(0, 64, 9, 0, np.float32)
     H = oracle.aca_rect(t, 15.0, 12.0, 128.0, 1.0, normalize=False)
