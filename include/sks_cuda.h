@@ -204,7 +204,14 @@ int sks_cuda_curand_mrg32k3a_u32(uint32_t *out, int64_t n, uint64_t seed, void *
  * reduced to best_key[pair] = max(count<<32 | (0xFFFFFFFF - hyp)).  best_key
  * is MAX-combined into the caller's array (zero it before the first call), so
  * several calls / several GPUs can cover disjoint hypothesis ranges and be
- * merged with an integer max-reduce.  No per-hypothesis H touches HBM. */
+ * merged with an integer max-reduce.  No per-hypothesis H touches HBM.
+ * Inlier rule (this project's definition; mirrored bit for bit by the CPU oracle):
+ * forward transfer error |proj(x) - X|^2 < thr2, evaluated division-free as
+ *   it = 1/sqrtf(thr2); g = H with rows 1-2 scaled by it; Xs = X*it, Ys = Y*it;
+ *   u,v,w = fma chains of g on (x, y, 1); du = fma(-Xs,w,u); dv = fma(-Ys,w,v);
+ *   inlier <=> fma(-w, w, fma(dv,dv,du*du)) < 0      (NaN / inf are never inliers)
+ * thr2 is the squared pixel threshold; keep it within ~1e-30..1e30 so that the folded
+ * operands stay finite. */
 int sks_cuda_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
                             const uint32_t *samples, uint32_t hyp_stride, uint32_t hyp_begin,
                             uint32_t hyp_count, uint64_t seed, float thr2,
