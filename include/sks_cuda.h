@@ -238,6 +238,12 @@ int sks_cuda_ransac_finalize_f32(const float *corr, int64_t n_pairs, int32_t n_p
                                  float thr2, const unsigned long long *best_key, float *H_best,
                                  uint32_t *inlier_count, uint8_t *inlier_mask, void *stream);
 
+/* Score GIVEN models with the same inlier rule: H [n_pairs][9] (h33-normalised or not) ->
+ * inlier_count [n_pairs] and / or inlier_mask [n_pairs][n_pts] (either may be NULL). */
+int sks_cuda_ransac_score_f32(const float *corr, int64_t n_pairs, int32_t n_pts, const float *H,
+                              float thr2, uint32_t *inlier_count, uint8_t *inlier_mask,
+                              void *stream);
+
 /* Post-RANSAC re-estimation hook (new; nothing like it in the reference): least-squares
  * homography of every pair from ALL matches flagged in inlier_mask [n_pairs][n_pts] (as written
  * by sks_cuda_ransac_finalize_f32): Hartley-normalised DLT normal equations accumulated and

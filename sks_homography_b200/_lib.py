@@ -71,6 +71,7 @@ _SIGS = {
     "sks_cuda_gather_aca_f64": (_int, [_vp, _u32, _vp, _u64, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "sks_cuda_gather_sks_f32": (_int, [_vp, _u32, _vp, _u64, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "sks_cuda_gather_sks_f64": (_int, [_vp, _u32, _vp, _u64, _vp, _i64, _int, _i64, _int, _vp, _vp]),
+    "sks_cuda_ransac_score_f32": (_int, [_vp, _i64, _i32, _vp, _f32, _vp, _vp, _vp]),
     "sks_cuda_ransac_refit_f32": (_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "sks_cuda_warp_grid_f32": (_int, [_vp, _i64, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp]),
     "sks_cuda_aca_rect_warp_grid_f32": (_int, [_vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _f32, _f32, _f32,

@@ -369,6 +369,34 @@ def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys
     return H, cnt, mask
 
 
+def ransac_score(corr: torch.Tensor, H: torch.Tensor, thr2: float, want_mask: bool = True):
+    """Inlier count (and mask) of GIVEN models H [P,9] under the library's inlier rule."""
+    L = lib()
+    corr, H = corr.contiguous(), H.contiguous()
+    P, n_pts, _ = corr.shape
+    cnt = torch.empty(P, dtype=torch.int32, device=corr.device)
+    mask = torch.empty((P, n_pts), dtype=torch.uint8, device=corr.device) if want_mask else None
+    with torch.cuda.device(corr.device):
+        L.check(L.c.sks_cuda_ransac_score_f32(_ptr(corr), P, n_pts, _ptr(H), thr2, _ptr(cnt), _ptr(mask),
+                                              _stream_ptr(corr)), "sks_cuda_ransac_score_f32")
+    return cnt, mask
+
+
+def ransac_polish(corr: torch.Tensor, H: torch.Tensor, thr2: float, iters: int = 2):
+    """LO-style polishing of RANSAC winners, entirely on the device: score -> least-squares refit on
+    the inlier mask -> score again, keeping a refit only where it explains MORE matches; repeated
+    `iters` times.  Returns (H [P,9], inlier_count [P], mask [P,n_pts])."""
+    cnt, mask = ransac_score(corr, H, thr2)
+    for _ in range(iters):
+        H2, used = ransac_refit(corr, mask, H)
+        cnt2, mask2 = ransac_score(corr, H2, thr2)
+        better = cnt2 > cnt
+        H = torch.where(better[:, None], H2, H)
+        mask = torch.where(better[:, None], mask2, mask)
+        cnt = torch.where(better, cnt2, cnt)
+    return H, cnt, mask
+
+
 def ransac_refit(corr: torch.Tensor, mask: torch.Tensor, H: torch.Tensor):
     """Least-squares re-estimation of every pair's homography from all matches flagged in
     `mask` [P, n_pts] (uint8, as returned by ransac_finalize(..., want_mask=True)); pairs

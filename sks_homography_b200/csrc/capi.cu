@@ -491,7 +491,21 @@ int sks_cuda_ransac_finalize_shard_f32(const float* corr, int64_t pair_begin, in
     if (n_pairs == 0) return SKS_OK;
     k_ransac_finalize<<<(unsigned)n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(corr), n_pts, samples, hyp_stride, seed_key(seed), thr2,
-        best_key, H_best, inlier_count, inlier_mask, pair_begin);
+        best_key, H_best, inlier_count, inlier_mask, pair_begin, nullptr);
+    return finish_launch();
+}
+
+int sks_cuda_ransac_score_f32(const float* corr, int64_t n_pairs, int32_t n_pts, const float* H, float thr2,
+                              uint32_t* inlier_count, uint8_t* inlier_mask, void* stream)
+{
+    if (corr == nullptr || H == nullptr || n_pairs < 0 || n_pts <= 0) return SKS_ERR_INVALID_ARG;
+    if (!aligned16(corr)) return SKS_ERR_UNALIGNED;
+    DevInfo dev;
+    if (int rc = device_info(dev)) return rc;
+    if (n_pairs == 0) return SKS_OK;
+    k_ransac_finalize<<<(unsigned)n_pairs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(corr), n_pts, nullptr, 0, 0, thr2, nullptr, nullptr, inlier_count,
+        inlier_mask, 0, H);
     return finish_launch();
 }
 

@@ -405,22 +405,30 @@ k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
                   const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint64_t key,
                   float thr2, const unsigned long long* __restrict__ best_key,
                   float* __restrict__ H_best, uint32_t* __restrict__ inlier_count,
-                  uint8_t* __restrict__ inlier_mask, int64_t pair_id_base)
+                  uint8_t* __restrict__ inlier_mask, int64_t pair_id_base,
+                  const float* __restrict__ H_given)
 {
     __shared__ float hs[9];
     __shared__ uint32_t total;
     const int64_t pair = blockIdx.x;
     const float4* corr_pair = corr + (size_t)pair * n_pts;
     if (threadIdx.x == 0) {
-        const uint32_t hyp = 0xFFFFFFFFu - (uint32_t)(best_key[pair] & 0xFFFFFFFFull);
-        uint32_t idx[4];
         float h[9];
-        ransac_sample(key, pair, pair_id_base, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
-        ransac_hypothesis(corr_pair, idx, h);
+        if (H_given != nullptr) {           // score the caller's models (post-RANSAC polishing)
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                h[k] = H_given[pair * 9 + k];
+        } else {
+            const uint32_t hyp = 0xFFFFFFFFu - (uint32_t)(best_key[pair] & 0xFFFFFFFFull);
+            uint32_t idx[4];
+            ransac_sample(key, pair, pair_id_base, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
+            ransac_hypothesis(corr_pair, idx, h);
+        }
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             hs[k] = h[k];
-            H_best[pair * 9 + k] = h[k];
+            if (H_best != nullptr)
+                H_best[pair * 9 + k] = h[k];
         }
         total = 0;
     }

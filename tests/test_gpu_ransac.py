@@ -215,3 +215,30 @@ def test_refit_on_inlier_mask(api, oracle, cuda):
     mask[0, :3] = 1                              # too few inliers: the 4-point winner is kept
     Hk, uk = api.ransac_refit(corr, mask, H)
     assert torch.equal(Hk[0], H[0]) and int(uk[0]) == 0
+
+
+def test_score_given_models_and_polish(api, oracle, cuda):
+    """sks_cuda_ransac_score_f32 == the oracle's count for arbitrary models; the LO-style polish
+    (score / refit / score, accept only improvements) never loses inliers and reproduces the
+    same loop run with the CPU ports."""
+    P, n_pts, n_hyp = 6, 2500, 1024
+    corr = api.synth_corr(P, n_pts, seed=14, device=cuda)
+    keys = api.ransac_keys(corr, n_hyp, seed=8, thr2=2.25)
+    H, cnt, mask = api.ransac_finalize(corr, n_hyp, 8, 2.25, keys, want_mask=True)
+    c2, m2 = api.ransac_score(corr, H, 2.25)
+    assert torch.equal(c2, cnt) and torch.equal(m2, mask)
+    Hp, cp, mp = api.ransac_polish(corr, H, 2.25, iters=2)
+    assert (cp >= cnt).all() and torch.equal(mp.sum(1).int(), cp)
+    # the same loop with the CPU ports
+    c_np = corr.cpu().numpy()
+    Hc, cc = H.cpu().numpy().copy(), cnt.cpu().numpy().astype(np.int64).copy()
+    mc = mask.cpu().numpy().copy()
+    for _ in range(2):
+        H2, _ = oracle.ransac_refit(c_np, mc, Hc)
+        for p in range(P):
+            n2 = oracle.ransac_count(H2[p], c_np[p], 2.25)
+            if n2 > cc[p]:
+                Hc[p], cc[p] = H2[p], n2
+                mc[p] = api.ransac_score(corr[p:p + 1], torch.from_numpy(H2[p:p + 1]).to(cuda), 2.25)[1][0].cpu().numpy()
+    assert np.array_equal(Hp.cpu().numpy().view(np.uint32), Hc.view(np.uint32))
+    assert np.array_equal(cp.cpu().numpy().astype(np.int64), cc)
