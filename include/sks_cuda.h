@@ -327,7 +327,8 @@ int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm);
 /* RANSAC kernel tuning: hypotheses carried per thread (2 or 4), scoring rounds
  * per CTA (a CTA scores rounds*256*hyps_per_thread hypothesis ids), and packed:
  * bits 0-1 = scorer (0: scalar FFMA; 1: sm_100a FFMA2/FMUL2 over two matches;
- * 2: FFMA2/FMUL2 over two hypotheses -- all three give the same bits),
+ * 2: FFMA2/FMUL2 over two hypotheses; 3 (default): as 1 with the inlier count kept on
+ * the FP32 pipe by a directed-rounding FFMA2 -- all four give the same bits),
  * bits 2.. = CTA size (0: 256, 1: 384, 2: 512 threads). */
 int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int packed);
 int sks_cuda_shutdown(void);

@@ -29,7 +29,8 @@ std::atomic<int> g_stages{4};
 std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
 std::atomic<int> g_wide{1};           // direct kernel: 256-bit loads/stores when 32-byte aligned
 std::atomic<int> g_ransac_hpt{2};     // hypotheses per thread in the RANSAC kernel (2 or 4)
-std::atomic<int> g_ransac_packed{1};  // scorer: 0 scalar FFMA, 1 FFMA2 over two matches, 2 FFMA2 over two hypotheses
+std::atomic<int> g_ransac_packed{3};  // scorer: 0 scalar FFMA, 1 FFMA2 over two matches, 2 FFMA2 over two hypotheses,
+                                      // 3 (default) = 1 with the inlier count on the FP32 pipe (FFMA2.RM)
 std::atomic<int> g_ransac_threads{256};
 std::atomic<int> g_ransac_rounds{8};  // rounds per CTA (chunk = rounds * 256 * hpt hypotheses)
 
@@ -429,7 +430,8 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
     using Kern = void (*)(const float4*, int64_t, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
                           uint32_t, uint32_t, uint64_t, float, unsigned long long*, int64_t);
 #define SKS_RANSAC_PICK(T)                                                                        \
-    (mode == 2 ? (hpt == 4 ? k_ransac_aca<4, 2, T> : k_ransac_aca<2, 2, T>)                       \
+    (mode == 3 ? (hpt == 4 ? k_ransac_aca<4, 3, T> : k_ransac_aca<2, 3, T>)                       \
+     : mode == 2 ? (hpt == 4 ? k_ransac_aca<4, 2, T> : k_ransac_aca<2, 2, T>)                     \
      : mode == 1 ? (hpt == 4 ? k_ransac_aca<4, 1, T> : k_ransac_aca<2, 1, T>)                     \
                  : (hpt == 4 ? k_ransac_aca<4, 0, T> : k_ransac_aca<2, 0, T>))
     const Kern kern = threads == 512 ? SKS_RANSAC_PICK(512)
@@ -643,7 +645,6 @@ int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int pack
         return SKS_ERR_INVALID_ARG;
     g_ransac_hpt.store(hyps_per_thread);
     g_ransac_rounds.store(rounds_per_cta);
-    if ((packed & 3) == 3) return SKS_ERR_INVALID_ARG;
     g_ransac_packed.store(packed & 3);
     const int t = packed >> 2;                       // bits 2.. select the CTA size
     g_ransac_threads.store(t == 1 ? 384 : t == 2 ? 512 : 256);

@@ -42,6 +42,14 @@
 #ifndef SKS_RANSAC_UNROLL
 #define SKS_RANSAC_UNROLL 8      // match PAIRS per unrolled iteration (measured best: 8, hypothesis-major)
 #endif
+#ifndef SKS_RANSAC_FP_UNROLL
+#define SKS_RANSAC_FP_UNROLL 2   // match pairs per unrolled iteration of the FP-count scorer (MODE 3); measured best of 1/2/3/4/6/8
+                                 // (profiles/r02_ransac_fp_sweep.log)
+#endif
+// resident CTAs per SM the register allocation must allow: a 64 KiB tile leaves room for three
+#ifndef SKS_RANSAC_MIN_CTAS
+#define SKS_RANSAC_MIN_CTAS(T) ((T) <= 256 ? 3 : (T) <= 384 ? 2 : 1)
+#endif
 #ifndef SKS_RANSAC_HYP_MAJOR
 #define SKS_RANSAC_HYP_MAJOR 1
 #endif
@@ -166,6 +174,89 @@ __device__ __forceinline__ uint32_t ransac_inlier2(const float2 (&g)[9], const f
 #endif
 }
 
+// Third form: the packed scorer above with the inlier COUNT kept on the FP32 pipe.
+// The two integer LEA.HI of ransac_inlier2 run on the 16-lane ALU pipe and cost 1.6-2
+// issue cycles each next to FFMA2 (profiles/r01_ubench_issue_mix.log); here the count
+// is one more packed FMA with directed rounding:
+//     cnt = fma_rd(acc, 2^-149, cnt)          cnt in [2^23, 2^24): ulp(cnt) = 1
+// |acc * 2^-149| < 2^-21 for every finite acc, the product is exact inside the FMA and
+// non-zero whenever acc != 0, so rounding toward -inf gives cnt - 1 exactly when
+// acc < 0 and cnt when acc >= +0 (or -0, which the IEEE test "acc < 0" of the oracle
+// rejects as well).  A NaN or infinite acc poisons cnt; the caller sees a non-finite
+// counter after the tile and recounts that hypothesis with the integer form, so the
+// result is the oracle's count in every case.
+__device__ __forceinline__ void ransac_inlier2_fp(const float2 (&g)[9], const float4 p0,
+                                                  const float4 p1, float2& cnt)
+{
+    const float2 x = make_float2(p0.x, p0.y), y = make_float2(p0.z, p0.w);
+    const float2 nX = make_float2(p1.x, p1.y), nY = make_float2(p1.z, p1.w);
+    const float2 u = __ffma2_rn(g[0], x, __ffma2_rn(g[1], y, g[2]));
+    const float2 v = __ffma2_rn(g[3], x, __ffma2_rn(g[4], y, g[5]));
+    const float2 w = __ffma2_rn(g[6], x, __ffma2_rn(g[7], y, g[8]));
+    const float2 du = __ffma2_rn(nX, w, u);
+    const float2 dv = __ffma2_rn(nY, w, v);
+    const float2 e = __ffma2_rn(dv, dv, __fmul2_rn(du, du));
+    const float2 nw = make_float2(__uint_as_float(__float_as_uint(w.x) ^ 0x80000000u),
+                                  __uint_as_float(__float_as_uint(w.y) ^ 0x80000000u));
+    const float2 acc = __ffma2_rn(nw, w, e);
+    const float tiny = __uint_as_float(1u);                       // 2^-149
+    cnt = __ffma2_rd(acc, make_float2(tiny, tiny), cnt);
+}
+constexpr float kRansacFpCount0 = 16777215.0f;
+// HPT hypotheses x one match pair, written phase by phase: every FFMA2 of a phase reads the
+// same match operand (y, x, -Xs / -Ys) in the same source slot, so consecutive instructions
+// take it from the operand-reuse cache and read at most two even and two odd registers -- a
+// packed FMA that needs a third register from one bank occupies the pipe for three cycles
+// instead of two (tools/ubench/count_ops.cu: 3.03 vs 2.04 cycles).  Same operations per
+// hypothesis x match as ransac_inlier2_fp, so the same bits.
+template <int HPT>
+__device__ __forceinline__ void ransac_score_pair_fp(const float (&g)[HPT][9], const float4 p0,
+                                                     const float4 p1, float2 (&fc)[HPT])
+{
+    const float2 x = make_float2(p0.x, p0.y), y = make_float2(p0.z, p0.w);
+    const float2 nX = make_float2(p1.x, p1.y), nY = make_float2(p1.z, p1.w);
+    float2 u[HPT], v[HPT], w[HPT];
+#define SKS_B(j, k) make_float2(g[j][k], g[j][k])
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {                       // phase 1: y in slot b
+        u[j] = __ffma2_rn(SKS_B(j, 1), y, SKS_B(j, 2));
+        v[j] = __ffma2_rn(SKS_B(j, 4), y, SKS_B(j, 5));
+        w[j] = __ffma2_rn(SKS_B(j, 7), y, SKS_B(j, 8));
+    }
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {                       // phase 2: x in slot b
+        u[j] = __ffma2_rn(SKS_B(j, 0), x, u[j]);
+        v[j] = __ffma2_rn(SKS_B(j, 3), x, v[j]);
+        w[j] = __ffma2_rn(SKS_B(j, 6), x, w[j]);
+    }
+#undef SKS_B
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {                       // phase 3: residuals, w[j] shared in slot b,
+        if (j & 1) {                                      // -Xs / -Ys shared in slot a across hypotheses
+            v[j] = __ffma2_rn(nY, w[j], v[j]);
+            u[j] = __ffma2_rn(nX, w[j], u[j]);
+        } else {
+            u[j] = __ffma2_rn(nX, w[j], u[j]);
+            v[j] = __ffma2_rn(nY, w[j], v[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < HPT; ++j)
+        u[j] = __fmul2_rn(u[j], u[j]);
+#pragma unroll
+    for (int j = 0; j < HPT; ++j)
+        u[j] = __ffma2_rn(v[j], v[j], u[j]);
+    const float tiny = __uint_as_float(1u);
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {
+        const float2 nw = make_float2(-w[j].x, -w[j].y);   // exact; ptxas folds it into FFMA2's operand negation
+        u[j] = __ffma2_rn(nw, w[j], u[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < HPT; ++j)
+        fc[j] = __ffma2_rd(u[j], make_float2(tiny, tiny), fc[j]);
+}
+
 // Second packed form: TWO HYPOTHESES per instruction, one match.  g[k] = (gA_k, gB_k)
 // are natural register pairs and the match scalars enter as broadcast operands
 // (SASS: Rn.F32), so no FFMA2 reads more than five registers (pair, scalar, pair)
@@ -196,56 +287,47 @@ __device__ __forceinline__ unsigned long long ransac_key(uint32_t count, uint32_
     return ((unsigned long long)count << 32) | (unsigned long long)(0xFFFFFFFFu - hyp);
 }
 
-// grid = (chunks_per_pair, n_pairs); each CTA scores hypothesis ids
-// [hyp_begin + chunk*chunk_size, +chunk_size) ∩ [hyp_begin, hyp_begin+hyp_count)
-// kRansacHpt: hypotheses carried per thread per round.  MODE 0: scalar FFMA scorer;
-// 1: two matches per FFMA2/FMUL2 (the tile is re-laid out in pairs on arrival);
-// 2: two hypotheses per FFMA2/FMUL2 (tile stays one match per 16 bytes).
-template <int kRansacHpt, int MODE, int kRansacThreads>
-__global__ void __launch_bounds__(kRansacThreads)
-k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, int32_t tile_pts,
-             const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
-             uint32_t hyp_count, uint32_t chunk_size, uint64_t key, float thr2,
-             unsigned long long* __restrict__ best_key, int64_t pair_id_base)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    float4* tile = reinterpret_cast<float4*>(smem);
-    __shared__ uint64_t bar;
-    __shared__ unsigned long long warp_best[kRansacThreads / 32];
+// State of a CTA's correspondence tile stream, shared by the scoring passes.
+struct RansacTileStream {
+    float4* tile;
+    uint64_t* bar;
+    const float4* corr_pair;
+    int32_t n_pts, tile_pts, n_tiles;
+    uint32_t phase;
+    bool resident;       // a single tile stays in shared memory for all rounds and passes
 
-    const int tid = threadIdx.x;
-    const int64_t pair = pair_base + blockIdx.y;
-    const float4* corr_pair = corr + (size_t)pair * n_pts;
-    const uint32_t c_lo = blockIdx.x * chunk_size;
-    if (c_lo >= hyp_count)
-        return;
-    const uint32_t c_hi = (hyp_count - c_lo < chunk_size) ? hyp_count : c_lo + chunk_size;
-    const int n_tiles = (n_pts + tile_pts - 1) / tile_pts;
-
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-    auto load_tile = [&](int tl) {   // thread 0: one bulk copy per tile
+    __device__ __forceinline__ void load(int tl) const   // one thread: one bulk copy per tile
+    {
         const int lo = tl * tile_pts;
         const int cnt = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
-        mbar_arrive_expect_tx(&bar, (uint32_t)cnt * 16u);
-        bulk_g2s(tile, corr_pair + lo, (uint32_t)cnt * 16u, &bar);
-    };
-    if (tid == 0)
-        load_tile(0);
-    bool resident = false;   // single tile stays in shared memory for all rounds
+        mbar_arrive_expect_tx(bar, (uint32_t)cnt * 16u);
+        bulk_g2s(tile, corr_pair + lo, (uint32_t)cnt * 16u, bar);
+    }
+};
 
-    constexpr bool PACKED = (MODE == 1);
+// One pass of a CTA over its hypothesis ids [c_lo, c_hi) of one pair: every thread carries HPT
+// hypotheses per round and walks the pair's tile(s).  MODE 0: scalar FFMA scorer; 1: two matches
+// per FFMA2/FMUL2 (the tile is re-laid out in pairs on arrival); 2: two hypotheses per
+// FFMA2/FMUL2 (tile stays one match per 16 bytes); 3: as 1 with the count on the FP32 pipe.
+// Returns true if an FP-pipe counter was poisoned by a NaN / infinite score (MODE 3 only): the
+// keys of this pass are then lower bounds and the caller repeats the pass with MODE 1.
+template <int kRansacHpt, int MODE, int kRansacThreads>
+__device__ __forceinline__ bool ransac_pass(RansacTileStream& ts, int64_t pair, int64_t pair_id_base,
+                                            const uint32_t* __restrict__ samples, uint32_t hyp_stride,
+                                            uint32_t hyp_begin, uint32_t c_lo, uint32_t c_hi, uint64_t key,
+                                            float it, unsigned long long& best)
+{
+    constexpr bool PACKED = (MODE == 1 || MODE == 3);
+    constexpr bool FPCOUNT = (MODE == 3);     // inlier count on the FP32 pipe (ransac_score_pair_fp)
     constexpr bool HYPPAIR = (MODE == 2);
     static_assert(!HYPPAIR || kRansacHpt % 2 == 0, "hypothesis pairs");
-    const float it = ransac_inv_thr(thr2);
-    unsigned long long best = 0ull;
+    const int tid = threadIdx.x;
+    float4* tile = ts.tile;
+    const int n_pts = ts.n_pts, tile_pts = ts.tile_pts, n_tiles = ts.n_tiles;
+    bool poisoned = false;
     for (uint32_t base = c_lo; base < c_hi; base += kRansacThreads * kRansacHpt) {
         float h[kRansacHpt][9];
-        float2 h2[PACKED ? kRansacHpt : HYPPAIR ? kRansacHpt / 2 : 1][9];
+        float2 h2[(PACKED && !FPCOUNT) ? kRansacHpt : HYPPAIR ? kRansacHpt / 2 : 1][9];
         uint32_t cnt[kRansacHpt], hyp[kRansacHpt];
         bool live[kRansacHpt];
 #pragma unroll
@@ -255,10 +337,25 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
             hyp[j] = hyp_begin + (live[j] ? local : c_lo);
             uint32_t idx[4];
             ransac_sample(key, pair, pair_id_base, hyp[j], samples, hyp_stride, (uint32_t)n_pts, idx);
-            ransac_hypothesis(corr_pair, idx, h[j]);
+            ransac_hypothesis(ts.corr_pair, idx, h[j]);
             ransac_scale_h(h[j], it);
             cnt[j] = 0;
-            if constexpr (PACKED) {
+            if constexpr (FPCOUNT) {
+                // A hypothesis with a non-finite entry (repeated or collinear sample) can never have an
+                // inlier: every entry feeds u, v or w, non-finite values propagate to e = +inf / NaN and
+                // acc = fma(-w, w, e) is then +inf or NaN.  Score it as the zero matrix instead (acc = +0
+                // for every finite match) so that it does not poison the FP-pipe counter; its key stays
+                // (0, id), as in the oracle.
+                uint32_t bad = 0;
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    bad |= ((__float_as_uint(h[j][k]) & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+                if (bad) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+                        h[j][k] = 0.0f;
+                }
+            } else if constexpr (PACKED) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k)
                     h2[j][k] = make_float2(h[j][k], h[j][k]);
@@ -274,14 +371,15 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
         for (int tl = 0; tl < n_tiles; ++tl) {
             const int lo = tl * tile_pts;
             const int np = (n_pts - lo < tile_pts) ? (n_pts - lo) : tile_pts;
-            if (!resident) {
-                mbar_wait(&bar, phase);
-                phase ^= 1;
-                resident = (n_tiles == 1);
+            if (!ts.resident) {
+                mbar_wait(ts.bar, ts.phase);
+                ts.phase ^= 1;
+                ts.resident = (n_tiles == 1);
                 if constexpr (PACKED) {
                     // re-lay the freshly landed AoS tile out in pairs, in place, with the
                     // targets scaled by 1/thr: (x0,x1,y0,y1)(-Xs0,-Xs1,-Ys0,-Ys1); an odd
-                    // tail is padded with a NaN target that can never be an inlier
+                    // tail is padded with a NaN target that can never be an inlier (the FP-pipe
+                    // count, which a NaN would poison, takes an odd last match through the integer form)
                     const float qnan = __int_as_float(0x7fffffff);
                     for (int p = tid; 2 * p < np; p += kRansacThreads) {
                         const float4 a = tile[2 * p];
@@ -299,7 +397,37 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
                 }
                 __syncthreads();
             }
-            if constexpr (PACKED) {
+            if constexpr (FPCOUNT) {
+                const int npair = np >> 1;                // an odd last match goes through the integer form
+                float2 fc[kRansacHpt];
+#pragma unroll
+                for (int j = 0; j < kRansacHpt; ++j)
+                    fc[j] = make_float2(kRansacFpCount0, kRansacFpCount0);
+                int i = 0;
+                for (; i + SKS_RANSAC_FP_UNROLL <= npair; i += SKS_RANSAC_FP_UNROLL) {
+                    float4 c[2 * SKS_RANSAC_FP_UNROLL];
+#pragma unroll
+                    for (int k = 0; k < 2 * SKS_RANSAC_FP_UNROLL; ++k)
+                        c[k] = tile[2 * i + k];   // warp-uniform address: broadcast
+#pragma unroll
+                    for (int k = 0; k < SKS_RANSAC_FP_UNROLL; ++k)
+                        ransac_score_pair_fp<kRansacHpt>(h, c[2 * k], c[2 * k + 1], fc);
+                }
+                for (; i < npair; ++i)
+                    ransac_score_pair_fp<kRansacHpt>(h, tile[2 * i], tile[2 * i + 1], fc);
+#pragma unroll
+                for (int j = 0; j < kRansacHpt; ++j) {
+                    const float dx = __fsub_rn(kRansacFpCount0, fc[j].x);   // exact when healthy
+                    const float dy = __fsub_rn(kRansacFpCount0, fc[j].y);
+                    const bool ok = dx >= 0.0f && dx <= 8388607.0f && dy >= 0.0f && dy <= 8388607.0f;
+                    cnt[j] += ok ? (uint32_t)dx + (uint32_t)dy : 0u;   // poisoned: a lower bound
+                    poisoned = poisoned || !ok;
+                    if (np & 1) {
+                        const float4 a = tile[np - 1], b = tile[np];
+                        cnt[j] += ransac_inlier(h[j], make_float4(a.x, a.z, b.x, b.z));
+                    }
+                }
+            } else if constexpr (PACKED) {
                 const int npair = (np + 1) >> 1;
                 int i = 0;
                 for (; i + SKS_RANSAC_UNROLL <= npair; i += SKS_RANSAC_UNROLL) {
@@ -371,7 +499,7 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
                 const bool more = (tl + 1 < n_tiles) ||
                                   (base + kRansacThreads * kRansacHpt < c_hi);
                 if (tid == 0 && more)
-                    load_tile((tl + 1) % n_tiles);
+                    ts.load((tl + 1) % n_tiles);
             }
         }
 #pragma unroll
@@ -380,6 +508,63 @@ k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, 
                 const unsigned long long k = ransac_key(cnt[j], hyp[j]);
                 best = k > best ? k : best;
             }
+    }
+    return poisoned;
+}
+
+// grid = (chunks_per_pair, n_pairs); each CTA scores hypothesis ids
+// [hyp_begin + chunk*chunk_size, +chunk_size) ∩ [hyp_begin, hyp_begin+hyp_count)
+// kRansacHpt: hypotheses carried per thread per round; MODE: see ransac_pass.  MODE 3 keeps its
+// hot loop free of cold code: if any FP-pipe counter of the CTA was poisoned (overflowing or
+// non-finite matches -- never on sane image coordinates), the CTA repeats its chunk with the
+// integer-count scorer of MODE 1 on the same packed tile and the keys are max-combined, which
+// gives the oracle's keys in every case.
+template <int kRansacHpt, int MODE, int kRansacThreads>
+__global__ void __launch_bounds__(kRansacThreads, SKS_RANSAC_MIN_CTAS(kRansacThreads))
+k_ransac_aca(const float4* __restrict__ corr, int64_t pair_base, int32_t n_pts, int32_t tile_pts,
+             const uint32_t* __restrict__ samples, uint32_t hyp_stride, uint32_t hyp_begin,
+             uint32_t hyp_count, uint32_t chunk_size, uint64_t key, float thr2,
+             unsigned long long* __restrict__ best_key, int64_t pair_id_base)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ unsigned long long warp_best[kRansacThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t pair = pair_base + blockIdx.y;
+    const uint32_t c_lo = blockIdx.x * chunk_size;
+    if (c_lo >= hyp_count)
+        return;
+    const uint32_t c_hi = (hyp_count - c_lo < chunk_size) ? hyp_count : c_lo + chunk_size;
+
+    RansacTileStream ts;
+    ts.tile = reinterpret_cast<float4*>(smem);
+    ts.bar = &bar;
+    ts.corr_pair = corr + (size_t)pair * n_pts;
+    ts.n_pts = n_pts;
+    ts.tile_pts = tile_pts;
+    ts.n_tiles = (n_pts + tile_pts - 1) / tile_pts;
+    ts.phase = 0;
+    ts.resident = false;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0)
+        ts.load(0);
+
+    const float it = ransac_inv_thr(thr2);
+    unsigned long long best = 0ull;
+    const bool poisoned = ransac_pass<kRansacHpt, MODE, kRansacThreads>(
+        ts, pair, pair_id_base, samples, hyp_stride, hyp_begin, c_lo, c_hi, key, it, best);
+    if constexpr (MODE == 3) {
+        if (__syncthreads_or(poisoned ? 1 : 0)) {      // cold: exact repeat with the integer count
+            if (!ts.resident && tid == 0)
+                ts.load(0);                            // multi-tile stream: start over at tile 0
+            ransac_pass<kRansacHpt, 1, kRansacThreads>(ts, pair, pair_id_base, samples, hyp_stride,
+                                                       hyp_begin, c_lo, c_hi, key, it, best);
+        }
     }
     // CTA-wide max: shuffles inside the warp, shared memory across warps
 #pragma unroll

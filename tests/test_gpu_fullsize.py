@@ -120,8 +120,8 @@ def test_config5_ransac_1024x4096x65536(api, sks, oracle, cuda):
     got = api.ransac_keys(sub, n_hyp, seed, thr2, None, lo, 1000).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, win) and int(win[0]) == int(full[0])
     try:
-        for hpt, mode in ((4, 1), (2, 2), (4, 2), (2, 0)):
+        for hpt, mode in ((2, 1), (4, 1), (2, 2), (4, 2), (2, 0), (4, 3)):
             assert sks.c.sks_cuda_set_ransac_tuning(hpt, 8, mode) == 0
             assert torch.equal(api.ransac_keys(corr[:128], n_hyp, seed, thr2), full[:128]), (hpt, mode)
     finally:
-        sks.c.sks_cuda_set_ransac_tuning(2, 8, 1)
+        sks.c.sks_cuda_set_ransac_tuning(2, 8, 3)

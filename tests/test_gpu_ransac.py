@@ -79,10 +79,10 @@ def test_dist_driver_single_rank(api, cuda):
     assert torch.equal(cnt.long(), kc) and torch.equal(hyp, kh)
 
 
-@pytest.mark.parametrize("packed", [0, 1, 2])
+@pytest.mark.parametrize("packed", [0, 1, 2, 3])
 @pytest.mark.parametrize("n_pts,n_hyp", [(4096, 1024), (1001, 777), (9001, 600), (3, 40)])
 def test_kernel_variants_match_oracle(api, sks, oracle, cuda, n_pts, n_hyp, packed):
-    """Scalar, match-pair FFMA2 and hypothesis-pair FFMA2 scorers, 2 or 4 hypotheses per thread: same keys."""
+    """Scalar, match-pair FFMA2, hypothesis-pair FFMA2 and FP-pipe-count (3) scorers, 2 or 4 hypotheses per thread: same keys."""
     corr = api.synth_corr(4, n_pts, seed=31, inlier_permille=600, device=cuda)
     want = oracle.ransac(corr.cpu().numpy(), n_hyp, seed=13, thr2=2.25)
     try:
@@ -90,10 +90,10 @@ def test_kernel_variants_match_oracle(api, sks, oracle, cuda, n_pts, n_hyp, pack
             assert sks.c.sks_cuda_set_ransac_tuning(hpt, 3, packed) == 0
             assert np.array_equal(u64(api.ransac_keys(corr, n_hyp, seed=13, thr2=2.25)), want)
     finally:
-        sks.c.sks_cuda_set_ransac_tuning(2, 8, 1)
+        sks.c.sks_cuda_set_ransac_tuning(2, 8, 3)
 
 
-@pytest.mark.parametrize("hpt,packed", [(2, 0), (4, 0), (2, 1), (4, 1), (2, 2), (4, 2)])
+@pytest.mark.parametrize("hpt,packed", [(2, 0), (4, 0), (2, 1), (4, 1), (2, 2), (4, 2), (2, 3), (4, 3)])
 def test_nonfinite_scores_are_never_inliers(api, sks, oracle, cuda, hpt, packed):
     """Overflowing / NaN hypotheses and matches: the GPU reads the inlier bit off the
     sign of acc, the oracle evaluates acc < 0; both must ignore NaN and +-inf alike."""
@@ -116,7 +116,7 @@ def test_nonfinite_scores_are_never_inliers(api, sks, oracle, cuda, hpt, packed)
             got[:, j] = (u64(k) >> np.uint64(32)).astype(np.uint32)
             assert np.array_equal(got[:, j], counts[:, j])
     finally:
-        sks.c.sks_cuda_set_ransac_tuning(2, 8, 1)
+        sks.c.sks_cuda_set_ransac_tuning(2, 8, 3)
 
 
 def test_more_pairs_than_one_grid_dimension(api, oracle, cuda):

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One lease script for every GPU session of this repo: gpurun -- 'bash tools/gpu_session.sh <stage> ...'
+# Every stage writes its logs under gpurun_out/ (merged back by gpurun).
+mkdir -p gpurun_out
+for stage in "$@"; do
+case "$stage" in
+  ransac_tests) timeout 900 python -m pytest tests/test_gpu_ransac.py -m gpu -q -x --timeout 600 2>&1 | tail -5 | tee gpurun_out/ransac_tests.log ;;
+  ransac_sweep) timeout 900 python tools/ransac_sweep.py 2>&1 | tee gpurun_out/ransac_sweep.log ;;
+  tests)        timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 2>&1 | tail -8 | tee gpurun_out/tests.log ;;
+  smoke)        timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log ;;
+  bench)        timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json ;;
+  bench_ref)    timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
+  sanitizer)    timeout 900 bash tools/sanitize.sh 2>&1 | tail -40 ;;
+  torch_ref)    timeout 600 python tools/torch_reference_gpu.py 2>&1 | tee gpurun_out/torch_reference_gpu.log ;;
+  bench_ransac) timeout 900 python bench.py --workload ransac --steps 5 > gpurun_out/bench_ransac.json 2> gpurun_out/bench_ransac.err; tail -c 2500 gpurun_out/bench_ransac.json ;;
+  ncu_ransac)   for cfg in "3 2" "3 4" "1 2"; do set -- $cfg; timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_ransac_aca -s 1 -c 1 -f -o gpurun_out/ransac_m$1_h$2 python tools/ransac_once.py 444 $1 $2 > gpurun_out/ncu_ransac_m$1_h$2.log 2>&1; tail -2 gpurun_out/ncu_ransac_m$1_h$2.log; done ;;
+  *) echo "unknown stage $stage" ;;
+esac
+done

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """torchrun test of the NVLink peer max-reduce against the NCCL all-reduce:
-   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/peer_reduce_test.py"""
+   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/peer_reduce_probe.py"""
 import os, sys, time
 import torch
 import torch.distributed as dist

@@ -10,19 +10,32 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "tools", "_variants")
-VARIANTS = {}
-for u in (2, 4, 8):
-    VARIANTS[f"rs_u{u}"] = [f"-DSKS_RANSAC_UNROLL={u}"]
+CAP2 = "-DSKS_RANSAC_MIN_CTAS(T)=((T)<=256?3:2)"
+VARIANTS = {"rs_base": []}
+for u in (1, 2, 3, 4, 6):
+    VARIANTS[f"rs_fp_u{u}"] = [f"-DSKS_RANSAC_FP_UNROLL={u}", CAP2]
+EXTRA = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+for e in EXTRA:                      # --variant=tag:-DX=1,-DY=2
+    tag, defs = e.split(":", 1)
+    VARIANTS[tag] = defs.split(",")
 
 if "--build" in sys.argv:
     from sks_homography_b200 import build as b
     os.makedirs(VDIR, exist_ok=True)
+    for f in glob.glob(os.path.join(VDIR, "*.so")):
+        os.remove(f)
     for tag, defs in VARIANTS.items():
         out = os.path.join(VDIR, f"libsks_cuda_{tag}.so")
         cmd = [b.nvcc()] + b.NVCC_FLAGS + defs + ["-Xptxas", "-v", "-o", out] + [os.path.join(b.CSRC, f) for f in b.SOURCES]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        regs = [l for l in r.stderr.splitlines() if "registers" in l]
-        print(tag, "ok" if r.returncode == 0 else r.stderr[-400:])
+        regs = {}
+        cur = None
+        for l in r.stderr.splitlines():
+            if "Compiling entry function" in l and "k_ransac_aca" in l:
+                cur = l.split("k_ransac_acaILi")[1][:14]
+            elif "Used" in l and cur:
+                regs[cur] = l.split("Used ")[1].split(" ")[0]; cur = None
+        print(tag, "ok" if r.returncode == 0 else r.stderr[-400:], {k: v for k, v in regs.items() if "ELi3ELi256" in k or "ELi1ELi256" in k})
     sys.exit(0)
 
 import torch
@@ -33,21 +46,25 @@ P, n_pts, n_hyp = 256, 4096, 65536
 corr = api.synth_corr(P, n_pts, seed=11, device=dev)
 ref = api.ransac_keys(corr, n_hyp, 11, 2.25)
 st = torch.cuda.current_stream().cuda_stream
+CONFIGS = [(1, 2, 0), (3, 2, 0), (3, 4, 0), (3, 2, 1), (3, 2, 2)]
 for path in sorted(glob.glob(os.path.join(VDIR, "libsks_cuda_rs_*.so"))):
     L = _lib.SksCuda(path)
-    for mode, hpt, thr in [(1, 2, 0), (2, 2, 0), (2, 4, 0), (2, 2, 1), (2, 4, 1), (2, 2, 2), (2, 4, 2)]:
-        L.c.sks_cuda_set_ransac_tuning(hpt, 8 if hpt == 2 else 4, mode | (thr << 2))
-        keys = torch.zeros(P, dtype=torch.int64, device=dev)
-        run = lambda: L.check(L.c.sks_cuda_ransac_aca_f32(corr.data_ptr(), P, n_pts, None, n_hyp, 0, n_hyp, 11,
-                                                          2.25, keys.data_ptr(), st), "ransac")
-        run(); torch.cuda.synchronize()
-        ok = bool(torch.equal(keys, ref))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            run()
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
-        tf = P * n_hyp * (103 + 21.0 * n_pts) / ms / 1e9
-        print(f"{os.path.basename(path):24s} mode={mode} hpt={hpt} threads={(256, 384, 512)[thr]} {ms:8.3f} ms  "
-              f"{tf:6.2f} TFLOP/s  {tf / 74.45:.3f} of peak  same_keys={ok}", flush=True)
+    for mode, hpt, thr in CONFIGS:
+        if "_fp" in path and mode != 3:
+            continue
+        for rounds in ((8,) if hpt == 2 else (4,)):
+            L.c.sks_cuda_set_ransac_tuning(hpt, rounds, mode | (thr << 2))
+            keys = torch.zeros(P, dtype=torch.int64, device=dev)
+            run = lambda: L.check(L.c.sks_cuda_ransac_aca_f32(corr.data_ptr(), P, n_pts, None, n_hyp, 0, n_hyp, 11,
+                                                              2.25, keys.data_ptr(), st), "ransac")
+            run(); torch.cuda.synchronize()
+            ok = bool(torch.equal(keys, ref))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                run()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            tf = P * n_hyp * (103 + 21.0 * n_pts) / ms / 1e9
+            print(f"{os.path.basename(path):24s} mode={mode} hpt={hpt} rounds={rounds} threads={(256, 384, 512)[thr]} "
+                  f"{ms:8.3f} ms  {tf:6.2f} TFLOP/s  {tf / 74.45:.3f} of peak  same_keys={ok}", flush=True)
