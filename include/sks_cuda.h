@@ -43,9 +43,10 @@
 extern "C" {
 #endif
 
-#define SKS_CUDA_ABI_VERSION 1
+#define SKS_CUDA_ABI_VERSION 2
 
-enum { SKS_OK = 0, SKS_ERR_INVALID_ARG = -1, SKS_ERR_UNALIGNED = -2, SKS_ERR_NO_DEVICE = -3 };
+enum { SKS_OK = 0, SKS_ERR_INVALID_ARG = -1, SKS_ERR_UNALIGNED = -2, SKS_ERR_NO_DEVICE = -3,
+       SKS_ERR_NO_PEER_ACCESS = -4 /* multi-GPU entry: a device cannot map the primary's memory */ };
 enum { SKS_LAYOUT_AOS = 0, SKS_LAYOUT_SOA = 1 };
 enum {
     SKS_FLAG_NORMALIZE = 1 /* divide out h33 as MOD/ACA_SKS.cpp:94-98 does; without it the
@@ -143,6 +144,14 @@ int sks_host_ransac_aca_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
                             const uint32_t *samples, uint32_t n_hyp, uint64_t seed, float thr2,
                             float *H_best, uint32_t *inlier_count, uint8_t *inlier_mask,
                             unsigned long long *best_key);
+/* The same over `ngpu` GPUs of this process (0 = all visible): one H2D copy to the current
+ * device, then the flow of sks_cuda_ransac_aca_multi_f32 below.  sks_host_ransac_aca_f32
+ * itself takes this route when sks_host_set_device_count(g != 1) is in effect, which is how
+ * sks::runRansac_ACA (include/sks_homography.hpp) reaches all GPUs of a box. */
+int sks_host_ransac_aca_multi_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                                  const uint32_t *samples, uint32_t n_hyp, uint64_t seed,
+                                  float thr2, int ngpu, float *H_best, uint32_t *inlier_count,
+                                  uint8_t *inlier_mask, unsigned long long *best_key);
 /* In-process multi-GPU driver for the host-pointer entry points: shard every batch
  * contiguously over `count` GPUs (devices 0..count-1; 0 = all visible; default 1 =
  * the current device only), one host thread and one PCIe link per GPU, no
@@ -199,7 +208,9 @@ int sks_cuda_curand_mrg32k3a_u32(uint32_t *out, int64_t n, uint64_t seed, void *
  * corr: [n_pairs][n_pts][4] = (x,y,X,Y) fp32.  Hypothesis ids
  * [hyp_begin, hyp_begin+hyp_count) of every pair are generated (4 indices
  * u32 % n_pts from the counter RNG keyed (seed, pair, hyp), or read from
- * samples[n_pairs][hyp_stride][4] if non-NULL), solved with the bit-exact fp32
+ * samples[n_pairs][hyp_stride][4] if non-NULL -- entries are reduced % n_pts like the
+ * reference's get_rand_list, GPU.cu:55-58, so a raw 32-bit stream such as the output of
+ * sks_cuda_curand_mrg32k3a_u32 is a valid list), solved with the bit-exact fp32
  * ACA, scored against the pair's correspondences held in shared memory and
  * reduced to best_key[pair] = max(count<<32 | (0xFFFFFFFF - hyp)).  best_key
  * is MAX-combined into the caller's array (zero it before the first call), so
@@ -232,11 +243,31 @@ int sks_cuda_ransac_finalize_shard_f32(const float *corr, int64_t pair_begin, in
                                        void *stream);
 /* Recompute the winning model of every pair from best_key (the sample list is
  * a pure function of the seed, so no H ever travels between GPUs): H_best
- * [n_pairs][9], inlier_count [n_pairs], optional inlier_mask [n_pairs][n_pts]. */
+ * [n_pairs][9], inlier_count [n_pairs], optional inlier_mask [n_pairs][n_pts].
+ * A pair whose key is still 0 (nothing was scored for it), or whose id lies outside an
+ * explicit sample list, has no model: H_best = NaN, inlier_count = 0, mask all 0. */
 int sks_cuda_ransac_finalize_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
                                  const uint32_t *samples, uint32_t hyp_stride, uint64_t seed,
                                  float thr2, const unsigned long long *best_key, float *H_best,
                                  uint32_t *inlier_count, uint8_t *inlier_mask, void *stream);
+
+/* Multi-GPU driver entry (SURVEY.md 8(b) "sks_cuda_*_multi(..., int ngpu)", 8(e) variant A) for
+ * callers that are ONE process, not one process per GPU: the whole estimate -- zero the keys,
+ * score hypothesis ids [0, n_hyp) of every pair, merge, rebuild the winners -- over `ngpu`
+ * devices (the current one, which owns corr / samples and all outputs, plus the next ngpu-1 in
+ * index order; 0 = all visible).  Device k scores the k-th contiguous shard of the hypothesis
+ * ids, reading the matches straight from the current device's memory over NVLink peer access
+ * (nothing is replicated), and max-combines its winners into best_key with system-scope
+ * atomics; CUDA events order the devices' streams, so the call only enqueues, like every other
+ * sks_cuda_* entry: results are valid when `stream` reaches the end of the enqueued work.  No
+ * NCCL, no IPC.  best_key [n_pairs] is overwritten (not max-combined).  H_best may be NULL to
+ * skip the finalize step.  Results are bit-identical to ngpu = 1.  Fails with
+ * SKS_ERR_NO_PEER_ACCESS where a device cannot map the current device's memory. */
+int sks_cuda_ransac_aca_multi_f32(const float *corr, int64_t n_pairs, int32_t n_pts,
+                                  const uint32_t *samples, uint32_t n_hyp, uint64_t seed,
+                                  float thr2, int ngpu, unsigned long long *best_key,
+                                  float *H_best, uint32_t *inlier_count, uint8_t *inlier_mask,
+                                  void *stream);
 
 /* Score GIVEN models with the same inlier rule: H [n_pairs][9] (h33-normalised or not) ->
  * inlier_count [n_pairs] and / or inlier_mask [n_pairs][n_pts] (either may be NULL). */
@@ -286,7 +317,11 @@ int sks_cuda_synth_corr_f32(float *corr, int64_t pair_begin, int64_t n_pairs, in
  * peer's.  A reduce is then sks_cuda_peer_push_max (system-scope atomicMax of
  * the local keys into every rank's block over NVLink + arrival signal) followed
  * by sks_cuda_peer_wait (bounded device-side wait for all `world` arrivals, then
- * the reduced keys are copied to keys_out; *status_dev = 1 on timeout).  `epoch`
+ * the reduced keys are copied to keys_out).  On a timeout *status_dev is set to 1 -- it is
+ * never cleared by the library, so zero it once and poll it; it may live in pinned host
+ * memory -- and keys_out is left UNTOUCHED: a partial max is never returned.  A timeout is
+ * fatal for the exchange (the arrival counters no longer line up): free and re-allocate the
+ * blocks, or fall back to an all-reduce.  `epoch`
  * counts reduces since allocation (0, 1, 2, ...) and must advance in lock-step
  * on all ranks; peer_blocks[g] is rank g's block as mapped in THIS process
  * (peer_blocks[rank] = the own block). */

@@ -79,6 +79,16 @@ inline int runRansac_ACA(const float* corr, std::int64_t n_pairs, std::int32_t n
                                    inlier_mask, nullptr);
 }
 
+// The same over `ngpu` GPUs of this process (0 = every visible GPU): hypothesis ids sharded,
+// winners merged over NVLink inside libsks_cuda, bit-identical to one GPU.
+inline int runRansac_ACA_multi(const float* corr, std::int64_t n_pairs, std::int32_t n_pts, std::uint32_t n_hyp,
+                               std::uint64_t seed, float thr2, int ngpu, float* H_best,
+                               std::uint32_t* inlier_count = nullptr, std::uint8_t* inlier_mask = nullptr)
+{
+    return sks_host_ransac_aca_multi_f32(corr, n_pairs, n_pts, nullptr, n_hyp, seed, thr2, ngpu, H_best,
+                                         inlier_count, inlier_mask, nullptr);
+}
+
 }  // namespace sks
 
 // The reference keeps its competitor solvers in namespace cv; the one that is

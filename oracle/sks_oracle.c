@@ -445,9 +445,11 @@ void oracle_ransac_aca_shard_f32(const float *corr, int64_t pair_begin, int64_t 
         for (uint32_t j = 0; j < hyp_count; ++j) {
             const uint32_t hyp = hyp_begin + j;
             uint32_t idx[4];
-            if (samples)
+            if (samples) {   /* reduced modulo n_pts like the reference's get_rand_list (GPU.cu:55-58) */
                 memcpy(idx, samples + 4 * ((size_t)p * hyp_stride + hyp), sizeof idx);
-            else
+                for (int k = 0; k < 4; ++k)
+                    idx[k] %= (uint32_t)n_pts;
+            } else
                 oracle_ransac_sample(seed, pair_begin + p, hyp, n_pts, idx);
             float H[9];
             oracle_ransac_hypothesis_f32(c, idx, H);

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsks_cuda.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "sks_cuda.h")
 
-OK, ERR_INVALID_ARG, ERR_UNALIGNED, ERR_NO_DEVICE = 0, -1, -2, -3
+OK, ERR_INVALID_ARG, ERR_UNALIGNED, ERR_NO_DEVICE, ERR_NO_PEER_ACCESS = 0, -1, -2, -3, -4
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 FLAG_NORMALIZE = 1
 DIST_DEEP, DIST_IMAGE, DIST_DEEP_INT = 0, 1, 2
@@ -61,6 +61,8 @@ _SIGS = {
     "sks_host_aca_rect_f32": (_int, [_vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _int]),
     "sks_host_aca_rect_f64": (_int, [_vp, _vp, _f64, _f64, _f64, _f64, _vp, _i64, _int]),
     "sks_host_ransac_aca_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u64, _f32, _vp, _vp, _vp, _vp]),
+    "sks_host_ransac_aca_multi_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u64, _f32, _int, _vp, _vp, _vp, _vp]),
+    "sks_cuda_ransac_aca_multi_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u64, _f32, _int, _vp, _vp, _vp, _vp, _vp]),
     "sks_host_set_device_count": (_int, [_int]),
     "sks_host_set_chunk_bytes": (_int, [_i64]),
     "sks_host_alloc_pinned": (_int, [C.POINTER(_vp), _i64]),

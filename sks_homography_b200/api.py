@@ -312,6 +312,21 @@ def curand_mrg32k3a(n: int, seed: int = 11, device="cuda", out: torch.Tensor | N
 
 
 # ------------------------------------------------------------------- RANSAC
+def _check_samples(samples, corr, n_hyp: int):
+    """An explicit sample list must be [P, n_hyp, 4] 32-bit integers, contiguous, on corr's device
+    (the kernel reads it as uint4 rows; a wider dtype would be silently misread)."""
+    if samples is None:
+        return None
+    P = corr.shape[0]
+    if samples.dtype not in (torch.int32, torch.uint32):
+        raise TypeError(f"samples must be int32/uint32, got {samples.dtype}")
+    if samples.device != corr.device:
+        raise ValueError(f"samples on {samples.device}, correspondences on {corr.device}")
+    if samples.numel() != P * n_hyp * 4:
+        raise ValueError(f"samples has {samples.numel()} elements, expected P*n_hyp*4 = {P * n_hyp * 4}")
+    return samples.contiguous()
+
+
 def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
                 samples: torch.Tensor | None = None, hyp_begin: int = 0,
                 hyp_count: int | None = None, out: torch.Tensor | None = None,
@@ -322,6 +337,7 @@ def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     L = lib()
     corr = corr.contiguous()
     P, n_pts, _ = corr.shape
+    samples = _check_samples(samples, corr, n_hyp)
     hyp_count = n_hyp - hyp_begin if hyp_count is None else hyp_count
     if out is None:
         out = torch.zeros(P, dtype=torch.int64, device=corr.device)
@@ -334,7 +350,7 @@ def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
 
 
 def ransac_host(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
-                samples: torch.Tensor | None = None, want_mask: bool = False):
+                samples: torch.Tensor | None = None, want_mask: bool = False, ngpu: int | None = None):
     """Whole estimate from HOST tensors through sks_host_ransac_aca_f32: corr [P, n_pts, 4] fp32 in
     host memory (pinned or pageable) -> (H [P,9], count [P], mask [P,n_pts] | None, keys [P])."""
     L = lib()
@@ -346,10 +362,36 @@ def ransac_host(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     cnt = torch.empty(P, dtype=torch.int32)
     keys = torch.empty(P, dtype=torch.int64)
     mask = torch.empty((P, n_pts), dtype=torch.uint8) if want_mask else None
-    if samples is not None:
-        samples = samples.contiguous()
-    L.check(L.c.sks_host_ransac_aca_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed, thr2, _ptr(H),
-                                        _ptr(cnt), _ptr(mask), _ptr(keys)), "sks_host_ransac_aca_f32")
+    samples = _check_samples(samples, corr, n_hyp)
+    if ngpu is None:       # one GPU, or whatever sks_host_set_device_count() says
+        L.check(L.c.sks_host_ransac_aca_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed, thr2, _ptr(H),
+                                            _ptr(cnt), _ptr(mask), _ptr(keys)), "sks_host_ransac_aca_f32")
+    else:                  # in-library multi-GPU driver (0 = all visible GPUs)
+        L.check(L.c.sks_host_ransac_aca_multi_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed, thr2, ngpu,
+                                                  _ptr(H), _ptr(cnt), _ptr(mask), _ptr(keys)),
+                "sks_host_ransac_aca_multi_f32")
+    return H, cnt, mask, keys
+
+
+def ransac_multi(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, ngpu: int = 0,
+                 samples: torch.Tensor | None = None, want_mask: bool = False, finalize: bool = True):
+    """Whole estimate over `ngpu` GPUs of THIS process (0 = all visible) through
+    sks_cuda_ransac_aca_multi_f32: corr [P, n_pts, 4] lives on its own device, which also receives
+    every output; the other devices read it over NVLink peer access and merge their winners with
+    peer atomics (csrc/multi.cu).  Returns (H [P,9] | None, count [P] | None, mask | None, keys [P])."""
+    L = lib()
+    corr = corr.contiguous()
+    P, n_pts, _ = corr.shape
+    samples = _check_samples(samples, corr, n_hyp)
+    dev = corr.device
+    keys = torch.empty(P, dtype=torch.int64, device=dev)
+    H = torch.empty((P, 9), dtype=torch.float32, device=dev) if finalize else None
+    cnt = torch.empty(P, dtype=torch.int32, device=dev) if finalize else None
+    mask = torch.empty((P, n_pts), dtype=torch.uint8, device=dev) if (finalize and want_mask) else None
+    with torch.cuda.device(dev):
+        L.check(L.c.sks_cuda_ransac_aca_multi_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed, thr2, ngpu,
+                                                  _ptr(keys), _ptr(H), _ptr(cnt), _ptr(mask), _stream_ptr(corr)),
+                "sks_cuda_ransac_aca_multi_f32")
     return H, cnt, mask, keys
 
 
@@ -358,6 +400,9 @@ def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys
     L = lib()
     corr = corr.contiguous()
     P, n_pts, _ = corr.shape
+    samples = _check_samples(samples, corr, n_hyp)
+    if keys.dtype != torch.int64 or keys.numel() != P or keys.device != corr.device or not keys.is_contiguous():
+        raise ValueError("keys must be a contiguous int64 tensor of P elements on corr's device")
     H = torch.empty((P, 9), dtype=torch.float32, device=corr.device)
     cnt = torch.empty(P, dtype=torch.int32, device=corr.device)
     mask = torch.empty((P, n_pts), dtype=torch.uint8, device=corr.device) if want_mask else None

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsks_cuda.so")
-SOURCES = ["capi.cu", "host_api.cu"]
+SOURCES = ["capi.cu", "host_api.cu", "multi.cu"]
 HEADERS = ["strict.cuh", "solvers.cuh", "ptx.cuh", "stream_kernels.cuh", "synth.cuh", "ransac.cuh", "peer.cuh", "mrg32k3a.cuh", "warp.cuh", "refit.cuh",
            os.path.join("..", "..", "include", "sks_cuda.h")]
 

@@ -255,6 +255,7 @@ const char* sks_cuda_error_string(int status)
         case SKS_ERR_INVALID_ARG: return "invalid argument";
         case SKS_ERR_UNALIGNED: return "pointer not 16-byte aligned";
         case SKS_ERR_NO_DEVICE: return "no CUDA device (libsks_cuda has no CPU fallback)";
+        case SKS_ERR_NO_PEER_ACCESS: return "a device cannot access the primary device's memory (no P2P)";
         default: break;
     }
     return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown error";

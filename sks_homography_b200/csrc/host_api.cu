@@ -21,6 +21,8 @@
 
 #include "../../include/sks_cuda.h"
 
+extern "C" void sks_multi_shutdown_internal(void);   // csrc/multi.cu
+
 namespace {
 
 constexpr int kRing = 4;
@@ -47,8 +49,8 @@ struct Slot {
 struct HostCtx {
     int device = -1;
     std::mutex mu;                     // one batch at a time per device
-    int64_t cap_in = 0, cap_out = 0;   // bytes per device buffer
-    bool staged_in = false, staged_out = false;
+    int64_t cap_in[3] = {0, 0, 0}, cap_out = 0;   // bytes per device buffer
+    bool staged_in[3] = {false, false, false}, staged_out = false;
     Slot slot[kRing];
 };
 
@@ -92,11 +94,15 @@ int get_ctx(int dev, HostCtx** out)
     if (c == nullptr) {
         c = new HostCtx();
         c->device = dev;
-        g_ctx.push_back(c);
         for (Slot& s : c->slot) {
-            CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+            if (e != cudaSuccess) {      // never publish a half-initialised context
+                free_ctx(c);
+                return (int)e;
+            }
         }
+        g_ctx.push_back(c);
     }
     *out = c;
     return SKS_OK;
@@ -104,19 +110,22 @@ int get_ctx(int dev, HostCtx** out)
 
 // Grow the ring's device / pinned buffers.  Caller holds c->mu, so no batch is in
 // flight on these buffers.
-int ensure_capacity(HostCtx* c, int64_t need_in, int64_t need_out, bool stage_in, bool stage_out)
+int ensure_capacity(HostCtx* c, const int64_t* need_in, int n_in, int64_t need_out, bool stage_in,
+                    bool stage_out)
 {
-    if (need_in > c->cap_in) {
-        for (Slot& s : c->slot)
-            for (int k = 0; k < 3; ++k) {
-                if (s.d_in[k]) CK(cudaFree(s.d_in[k]));
-                s.d_in[k] = nullptr;
-                CK(cudaMalloc(&s.d_in[k], (size_t)need_in));
-                if (s.p_in[k]) CK(cudaFreeHost(s.p_in[k]));
-                s.p_in[k] = nullptr;
-            }
-        c->cap_in = need_in;
-        c->staged_in = false;
+    // input array k gets exactly what it needs (the M array of ACA-rect is a quarter of the
+    // corner array, and most calls have no third input at all)
+    for (int k = 0; k < n_in; ++k) {
+        if (need_in[k] <= c->cap_in[k]) continue;
+        for (Slot& s : c->slot) {
+            if (s.d_in[k]) CK(cudaFree(s.d_in[k]));
+            s.d_in[k] = nullptr;
+            CK(cudaMalloc(&s.d_in[k], (size_t)need_in[k]));
+            if (s.p_in[k]) CK(cudaFreeHost(s.p_in[k]));
+            s.p_in[k] = nullptr;
+        }
+        c->cap_in[k] = need_in[k];
+        c->staged_in[k] = false;
     }
     if (need_out > c->cap_out) {
         for (Slot& s : c->slot) {
@@ -129,12 +138,12 @@ int ensure_capacity(HostCtx* c, int64_t need_in, int64_t need_out, bool stage_in
         c->cap_out = need_out;
         c->staged_out = false;
     }
-    if (stage_in && !c->staged_in) {
-        for (Slot& s : c->slot)
-            for (int k = 0; k < 3; ++k)
-                CK(cudaHostAlloc(&s.p_in[k], (size_t)c->cap_in, cudaHostAllocDefault));
-        c->staged_in = true;
-    }
+    for (int k = 0; k < n_in; ++k)
+        if (stage_in && !c->staged_in[k]) {
+            for (Slot& s : c->slot)
+                CK(cudaHostAlloc(&s.p_in[k], (size_t)c->cap_in[k], cudaHostAllocDefault));
+            c->staged_in[k] = true;
+        }
     if (stage_out && !c->staged_out) {
         for (Slot& s : c->slot)
             CK(cudaHostAlloc(&s.p_out, (size_t)c->cap_out, cudaHostAllocDefault));
@@ -274,8 +283,9 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
     HostCtx* c = nullptr;
     if (int rc = get_ctx(dev, &c)) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (int rc = ensure_capacity(c, chunk * 8 * (int64_t)sizeof(T), chunk * 9 * (int64_t)sizeof(T),
-                                 stage_in, stage_out))
+    int64_t need_in[3] = {0, 0, 0};
+    for (int k = 0; k < n_in; ++k) need_in[k] = chunk * in_elems[k] * (int64_t)sizeof(T);
+    if (int rc = ensure_capacity(c, need_in, n_in, chunk * 9 * (int64_t)sizeof(T), stage_in, stage_out))
         return rc;
 
     if (stage_in || stage_out) {
@@ -377,30 +387,47 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
 
     const int64_t n_chunks = (int64_t)offs.size();
     int rc = SKS_OK;
+    auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == SKS_OK) rc = (int)e; return e == cudaSuccess; };
     for (int64_t ci = 0; ci < n_chunks && rc == SKS_OK; ++ci) {
         Slot& s = c->slot[ci % kRing];
         if ((rc = drain(s)) != SKS_OK) break;
         const int64_t off = offs[ci], cnt = cnts[ci];
-        for (int k = 0; k < n_in; ++k) {
+        for (int k = 0; k < n_in && rc == SKS_OK; ++k) {
             const size_t bytes = (size_t)cnt * in_elems[k] * sizeof(T);
             const T* hsrc = in[k] + off * in_elems[k];
             if (stage_in) {
                 parallel_copy(s.p_in[k], hsrc, bytes);
                 hsrc = static_cast<const T*>(s.p_in[k]);
             }
-            CK(cudaMemcpyAsync(s.d_in[k], hsrc, bytes, cudaMemcpyHostToDevice, s.stream));
+            cu(cudaMemcpyAsync(s.d_in[k], hsrc, bytes, cudaMemcpyHostToDevice, s.stream));
         }
+        if (rc != SKS_OK) break;
         rc = launch(s, cnt);
         if (rc != SKS_OK) break;
         T* hdst = stage_out ? static_cast<T*>(s.p_out) : out + off * 9;
-        CK(cudaMemcpyAsync(hdst, s.d_out, (size_t)cnt * 9 * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaEventRecord(s.done, s.stream));
+        if (!cu(cudaMemcpyAsync(hdst, s.d_out, (size_t)cnt * 9 * sizeof(T), cudaMemcpyDeviceToHost, s.stream)))
+            break;
+        if (!cu(cudaEventRecord(s.done, s.stream))) break;
         s.pending_off = off;
         s.pending_cnt = cnt;
+    }
+    if (rc != SKS_OK) {
+        // an enqueue failed mid-batch: nothing of this batch may stay in flight towards the
+        // caller's buffers, and the persistent context must not remember a pending chunk
+        for (Slot& s : c->slot) {
+            cudaStreamSynchronize(s.stream);
+            s.pending_off = -1;
+        }
+        cudaGetLastError();
+        return rc;
     }
     for (Slot& s : c->slot) {
         const int r2 = drain(s);
         if (rc == SKS_OK) rc = r2;
+        if (r2 != SKS_OK) {
+            cudaStreamSynchronize(s.stream);
+            s.pending_off = -1;
+        }
     }
     return rc;
 }
@@ -525,13 +552,17 @@ int sks_host_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts, c
                             uint32_t n_hyp, uint64_t seed, float thr2, float* H_best,
                             uint32_t* inlier_count, uint8_t* inlier_mask, unsigned long long* best_key)
 {
-    if (corr == nullptr || H_best == nullptr || n_pairs < 0 || n_pts <= 0) return SKS_ERR_INVALID_ARG;
+    if (corr == nullptr || H_best == nullptr || n_pairs < 0 || n_pts <= 0 || n_hyp == 0)
+        return SKS_ERR_INVALID_ARG;          // no hypotheses: there would be no model to return
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
         cudaGetLastError();
         return SKS_ERR_NO_DEVICE;
     }
     if (n_pairs == 0) return SKS_OK;
+    if (g_host_devices.load() != 1 && dev_count > 1)     // in-library multi-GPU driver (csrc/multi.cu)
+        return sks_host_ransac_aca_multi_f32(corr, n_pairs, n_pts, samples, n_hyp, seed, thr2, g_host_devices.load(),
+                                             H_best, inlier_count, inlier_mask, best_key);
     int dev = 0;
     CK(cudaGetDevice(&dev));
     RansacHostCtx* c = nullptr;
@@ -566,20 +597,25 @@ int sks_host_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts, c
     unsigned long long* d_key = static_cast<unsigned long long*>(c->buf[3]);
     uint32_t* d_samp = samples ? static_cast<uint32_t*>(c->buf[4]) : nullptr;
     uint8_t* d_mask = inlier_mask ? static_cast<uint8_t*>(c->buf[5]) : nullptr;
-    CK(cudaMemcpyAsync(d_corr, corr, need[0], cudaMemcpyHostToDevice, st));
-    if (samples) CK(cudaMemcpyAsync(d_samp, samples, need[4], cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(d_key, 0, need[3], st));
-    if (int rc = sks_cuda_ransac_aca_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, 0, n_hyp, seed, thr2, d_key, st))
-        return rc;
-    if (int rc = sks_cuda_ransac_finalize_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, seed, thr2, d_key, d_H,
-                                              d_cnt, d_mask, st))
-        return rc;
-    CK(cudaMemcpyAsync(H_best, d_H, need[1], cudaMemcpyDeviceToHost, st));
-    if (inlier_count) CK(cudaMemcpyAsync(inlier_count, d_cnt, need[2], cudaMemcpyDeviceToHost, st));
-    if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, d_mask, need[5], cudaMemcpyDeviceToHost, st));
-    if (best_key) CK(cudaMemcpyAsync(best_key, d_key, need[3], cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return SKS_OK;
+    int rc = SKS_OK;
+    auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == SKS_OK) rc = (int)e; return rc == SKS_OK; };
+    cu(cudaMemcpyAsync(d_corr, corr, need[0], cudaMemcpyHostToDevice, st));
+    if (rc == SKS_OK && samples) cu(cudaMemcpyAsync(d_samp, samples, need[4], cudaMemcpyHostToDevice, st));
+    if (rc == SKS_OK) cu(cudaMemsetAsync(d_key, 0, need[3], st));
+    if (rc == SKS_OK)
+        rc = sks_cuda_ransac_aca_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, 0, n_hyp, seed, thr2, d_key, st);
+    if (rc == SKS_OK)
+        rc = sks_cuda_ransac_finalize_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, seed, thr2, d_key, d_H, d_cnt,
+                                          d_mask, st);
+    if (rc == SKS_OK) cu(cudaMemcpyAsync(H_best, d_H, need[1], cudaMemcpyDeviceToHost, st));
+    if (rc == SKS_OK && inlier_count) cu(cudaMemcpyAsync(inlier_count, d_cnt, need[2], cudaMemcpyDeviceToHost, st));
+    if (rc == SKS_OK && inlier_mask) cu(cudaMemcpyAsync(inlier_mask, d_mask, need[5], cudaMemcpyDeviceToHost, st));
+    if (rc == SKS_OK && best_key) cu(cudaMemcpyAsync(best_key, d_key, need[3], cudaMemcpyDeviceToHost, st));
+    // success or not: no copy towards the caller's buffers may still be in flight on return
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (rc == SKS_OK && es != cudaSuccess) rc = (int)es;
+    if (rc != SKS_OK) cudaGetLastError();
+    return rc;
 }
 
 int sks_host_alloc_pinned(void** ptr, int64_t bytes)
@@ -615,11 +651,15 @@ int sks_host_set_device_count(int count)
 int sks_cuda_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (HostCtx* c : g_ctx) free_ctx(c);
+    for (HostCtx* c : g_ctx) {
+        { std::lock_guard<std::mutex> busy(c->mu); }   // wait for a batch that is still running on it
+        free_ctx(c);
+    }
     g_ctx.clear();
     int prev = 0;
     cudaGetDevice(&prev);
     for (RansacHostCtx* c : g_ransac_ctx) {
+        { std::lock_guard<std::mutex> busy(c->mu); }
         cudaSetDevice(c->device);
         for (void* b : c->buf)
             if (b) cudaFree(b);
@@ -628,6 +668,7 @@ int sks_cuda_shutdown(void)
     }
     g_ransac_ctx.clear();
     cudaSetDevice(prev);
+    sks_multi_shutdown_internal();
     return SKS_OK;
 }
 

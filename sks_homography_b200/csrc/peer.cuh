@@ -66,7 +66,10 @@ k_peer_push_max(const unsigned long long* __restrict__ local_keys, int64_t n_key
     }
 }
 
-// status: 0 = ok, 1 = timed out waiting for the peers (keys_out then holds a partial max)
+// status: set to 1 (and never cleared here) when the wait timed out; keys_out is then left
+// UNTOUCHED -- a partial max must not be mistaken for the reduced keys.  After a timeout the
+// exchange is unusable (the arrival counters no longer line up): the caller has to treat it as
+// fatal (dist.PeerReducer raises) and rebuild the blocks or fall back to the NCCL all-reduce.
 __global__ void __launch_bounds__(256)
 k_peer_wait_copy(PeerBlock* own, int world, uint64_t epoch, unsigned long long* __restrict__ keys_out,
                  int64_t n_keys, int* __restrict__ status, long long timeout_cycles)
@@ -85,11 +88,14 @@ k_peer_wait_copy(PeerBlock* own, int world, uint64_t epoch, unsigned long long* 
         }
         __threadfence_system();
         ok = good;
-        if (status != nullptr)
-            *status = good ? 0 : 1;
+        if (status != nullptr && !good) {
+            *reinterpret_cast<volatile int*>(status) = 1;
+            __threadfence_system();
+        }
     }
     __syncthreads();
-    (void)ok;
+    if (!ok)
+        return;
     const unsigned long long* src = peer_keys(own, epoch, n_keys);
     for (int64_t i = threadIdx.x; i < n_keys; i += blockDim.x)
         keys_out[i] = __ldcg(src + i);

@@ -79,7 +79,9 @@ __device__ __forceinline__ void ransac_sample(uint64_t key, int64_t pair, int64_
     if (samples != nullptr) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(samples) +
                               ((size_t)pair * hyp_stride + hyp));
-        idx[0] = v.x; idx[1] = v.y; idx[2] = v.z; idx[3] = v.w;
+        // reduced like the reference's sampler (get_rand_list: r % size, GPU.cu:55-58), so a raw
+        // 32-bit stream (e.g. sks_cuda_curand_mrg32k3a_u32) is a valid list; in-range lists unchanged
+        idx[0] = v.x % n_pts; idx[1] = v.y % n_pts; idx[2] = v.z % n_pts; idx[3] = v.w % n_pts;
     } else {
         const uint64_t ctr = ((uint64_t)(pair + pair_id_base) << 32) | (uint64_t)hyp;
 #pragma unroll
@@ -604,10 +606,20 @@ k_ransac_finalize(const float4* __restrict__ corr, int32_t n_pts,
             for (int k = 0; k < 9; ++k)
                 h[k] = H_given[pair * 9 + k];
         } else {
-            const uint32_t hyp = 0xFFFFFFFFu - (uint32_t)(best_key[pair] & 0xFFFFFFFFull);
-            uint32_t idx[4];
-            ransac_sample(key, pair, pair_id_base, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
-            ransac_hypothesis(corr_pair, idx, h);
+            // a key that is still zero (nothing was scored for this pair) decodes to the id
+            // 0xFFFFFFFF: no model -- NaN matrix, count 0 -- instead of a fabricated one
+            const unsigned long long bk = best_key[pair];
+            const uint32_t hyp = 0xFFFFFFFFu - (uint32_t)(bk & 0xFFFFFFFFull);
+            if (bk == 0ull || (samples != nullptr && hyp >= hyp_stride)) {
+                const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    h[k] = qnan;
+            } else {
+                uint32_t idx[4];
+                ransac_sample(key, pair, pair_id_base, hyp, samples, hyp_stride, (uint32_t)n_pts, idx);
+                ransac_hypothesis(corr_pair, idx, h);
+            }
         }
 #pragma unroll
         for (int k = 0; k < 9; ++k) {

@@ -111,7 +111,9 @@ class PeerReducer:
                     self.L.check(self.L.c.sks_cuda_peer_open(buf, C.byref(p)), "sks_cuda_peer_open")
                     self.blocks[g] = p
                     self._opened.append(p)
-            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            # sticky time-out flag in pinned host memory (device-visible under UVA): the wait kernel
+            # sets it to 1, the host reads it without synchronising the stream
+            self.status = torch.zeros(1, dtype=torch.int32).pin_memory()
             if self.world > 1:
                 dist.barrier(group=group)      # every block exists and is zeroed before the first push
 
@@ -119,6 +121,7 @@ class PeerReducer:
         """In-place global max of the packed keys (int64 view) across the ranks."""
         if keys.numel() != self.n_keys or keys.dtype != torch.int64 or not keys.is_contiguous():
             raise ValueError("keys must be a contiguous int64 tensor of n_keys elements")
+        self.check()                   # a time-out of an EARLIER step is fatal for the exchange
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
             self.L.check(self.L.c.sks_cuda_peer_push_max(keys.data_ptr(), self.n_keys, self.blocks, self.world,
@@ -130,11 +133,24 @@ class PeerReducer:
         return keys
 
     def timed_out(self) -> bool:
-        return bool(self.status.item())
+        """Synchronises the device, then reports whether any wait so far timed out."""
+        torch.cuda.synchronize(self.device)
+        return bool(self.status[0].item())
 
-    def close(self) -> None:
+    def check(self) -> None:
+        """Raise if a wait timed out (no synchronisation: sees every step that has completed).
+        After a time-out the keys of that step were left un-reduced and the arrival counters no
+        longer line up, so the reducer cannot be used again: rebuild it or use merge_keys()."""
+        if int(self.status[0]) != 0:
+            raise RuntimeError(
+                f"PeerReducer (rank {self.rank}/{self.world}): a peer did not arrive within "
+                f"{self.timeout_s} s; the keys of that step are NOT reduced and the exchange is "
+                "unusable -- rebuild the reducer or fall back to dist.merge_keys()")
+
+    def close(self, check: bool = True) -> None:
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
+            failed = int(self.status[0]) != 0
             if self.world > 1:
                 dist.barrier(group=self.group)
             for p in self._opened:
@@ -143,6 +159,8 @@ class PeerReducer:
             if self.own is not None:
                 self.L.c.sks_cuda_peer_free(self.own)
                 self.own = None
+        if check and failed:
+            raise RuntimeError("PeerReducer: a wait timed out during this session (keys of that step un-reduced)")
 
 
 def ransac_aca(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
@@ -155,6 +173,8 @@ def ransac_aca(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     keys = api.ransac_keys(corr, n_hyp, seed, thr2, samples, begin, count)
     if reducer is not None:
         reducer.max_reduce_(keys)      # NVLink peer atomics instead of the NCCL all-reduce
+        if reducer.timed_out():        # synchronises; the models below would otherwise differ per rank
+            reducer.check()
     else:
         merge_keys(keys, group)
     H, cnt, mask = api.ransac_finalize(corr, n_hyp, seed, thr2, keys, samples, want_mask)

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(sks):
     missing = [n for n in declared if not hasattr(raw, n)]
     assert not missing, missing
     assert set(_lib._SIGS) == set(declared)          # the binding covers the whole ABI
-    assert sks.c.sks_cuda_abi_version() == 1
+    assert sks.c.sks_cuda_abi_version() == 2
 
 
 def test_library_is_sm100a_with_bulk_copy_kernels(sks):

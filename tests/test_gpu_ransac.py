@@ -146,6 +146,69 @@ def test_peer_reducer_single_rank_epochs(api, cuda):
         red.close()
 
 
+def test_peer_wait_timeout_is_fatal_and_leaves_keys_untouched(api, sks, cuda):
+    """A wait for more arrivals than ever come (world = 2 on one rank) must time out, set the
+    sticky status flag, leave keys_out as it was, and make the reducer refuse further work."""
+    import ctypes as C
+    from sks_homography_b200 import dist as sd
+    red = sd.PeerReducer(64, cuda, timeout_s=0.05)
+    try:
+        keys = torch.arange(1, 65, dtype=torch.int64, device=cuda)
+        red.max_reduce_(keys)                                   # epoch 0, world 1: fine
+        assert not red.timed_out()
+        out = torch.full((64,), -7, dtype=torch.int64, device=cuda)
+        st = torch.cuda.current_stream(cuda).cuda_stream
+        sks.check(sks.c.sks_cuda_peer_push_max(keys.data_ptr(), 64, red.blocks, 1, 0, red.epoch, st), "push")
+        sks.check(sks.c.sks_cuda_peer_wait(red.own, 2, red.epoch, out.data_ptr(), 64, red.status.data_ptr(),
+                                           C.c_double(0.05), st), "wait")        # a second rank never arrives
+        assert red.timed_out()
+        assert bool((out == -7).all()), "keys_out must be untouched after a timeout"
+        with pytest.raises(RuntimeError, match="did not arrive"):
+            red.max_reduce_(keys)
+    finally:
+        red.close(check=False)
+
+
+def test_explicit_samples_are_reduced_modulo_n_pts(api, oracle, cuda):
+    """A raw 32-bit stream (here the cuRAND-compatible generator) is a valid sample list: entries
+    are taken % n_pts like the reference's get_rand_list (GPU.cu:55-58), on the GPU and in the oracle."""
+    P, n_pts, n_hyp = 3, 777, 400
+    corr = api.synth_corr(P, n_pts, seed=8, device=cuda)
+    raw = api.curand_mrg32k3a(P * n_hyp * 4, seed=11, device=cuda).view(P, n_hyp, 4)
+    assert int((raw.cpu().numpy().view(np.uint32) >= n_pts).sum()) > 0
+    keys = api.ransac_keys(corr, n_hyp, seed=0, thr2=2.25, samples=raw)
+    want = oracle.ransac(corr.cpu().numpy(), n_hyp, 0, 2.25, samples=raw.cpu().numpy().view(np.uint32))
+    assert np.array_equal(u64(keys), want)
+    reduced = torch.from_numpy((raw.cpu().numpy().view(np.uint32) % n_pts).astype(np.int32)).to(cuda)
+    assert torch.equal(api.ransac_keys(corr, n_hyp, seed=0, thr2=2.25, samples=reduced), keys)
+    H, cnt, _ = api.ransac_finalize(corr, n_hyp, 0, 2.25, keys, samples=raw)
+    kc, _ = api.decode_keys(keys)
+    assert torch.equal(cnt.long(), kc)
+
+
+def test_finalize_of_an_unscored_pair_is_no_model(api, cuda):
+    """best_key == 0 (nothing scored) must not decode to hypothesis 0xFFFFFFFF: NaN model, count 0."""
+    corr = api.synth_corr(2, 100, seed=8, device=cuda)
+    keys = api.ransac_keys(corr, 64, seed=1, thr2=2.25)
+    keys[1] = 0
+    H, cnt, mask = api.ransac_finalize(corr, 64, 1, 2.25, keys, want_mask=True)
+    assert bool(torch.isfinite(H[0]).all()) and int(cnt[0]) == int(keys[0] >> 32)
+    assert bool(torch.isnan(H[1]).all()) and int(cnt[1]) == 0 and int(mask[1].sum()) == 0
+    samples = torch.zeros((2, 64, 4), dtype=torch.int32, device=cuda)
+    H2, cnt2, _ = api.ransac_finalize(corr, 64, 1, 2.25, keys, samples=samples)
+    assert bool(torch.isnan(H2[1]).all()) and int(cnt2[1]) == 0
+
+
+def test_sample_list_validation(api, cuda):
+    corr = api.synth_corr(2, 100, seed=8, device=cuda)
+    with pytest.raises(TypeError):
+        api.ransac_keys(corr, 16, 1, 2.25, samples=torch.zeros((2, 16, 4), dtype=torch.int64, device=cuda))
+    with pytest.raises(ValueError):
+        api.ransac_keys(corr, 16, 1, 2.25, samples=torch.zeros((2, 15, 4), dtype=torch.int32, device=cuda))
+    with pytest.raises(ValueError):
+        api.ransac_keys(corr, 16, 1, 2.25, samples=torch.zeros((2, 16, 4), dtype=torch.int32))
+
+
 def test_host_pointer_entry_point(api, oracle, cuda):
     """sks_host_ransac_aca_f32: matches in host memory in, models / counts / masks / keys out."""
     P, n_pts, n_hyp = 3, 2000, 1500

@@ -14,6 +14,8 @@ case "$stage" in
   torch_ref)    timeout 600 python tools/torch_reference_gpu.py 2>&1 | tee gpurun_out/torch_reference_gpu.log ;;
   bench_ransac) timeout 900 python bench.py --workload ransac --steps 5 > gpurun_out/bench_ransac.json 2> gpurun_out/bench_ransac.err; tail -c 2500 gpurun_out/bench_ransac.json ;;
   ncu_ransac)   for cfg in "3 2" "3 4" "1 2"; do set -- $cfg; timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_ransac_aca -s 1 -c 1 -f -o gpurun_out/ransac_m$1_h$2 python tools/ransac_once.py 444 $1 $2 > gpurun_out/ncu_ransac_m$1_h$2.log 2>&1; tail -2 gpurun_out/ncu_ransac_m$1_h$2.log; done ;;
+  multi_tests)  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x --timeout 300 2>&1 | tail -15 | tee gpurun_out/multi_tests.log ;;
+  cpp_multi)    g++ -std=c++17 -O2 -I include tests/cpp/ransac_multi_main.cpp -o /tmp/ransac_multi -L sks_homography_b200 -lsks_cuda -Wl,-rpath,$PWD/sks_homography_b200 && timeout 300 /tmp/ransac_multi 1024 4096 65536 2>&1 | tee gpurun_out/cpp_multi.log ;;
   *) echo "unknown stage $stage" ;;
 esac
 done
