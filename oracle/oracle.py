@@ -22,13 +22,16 @@ REF_SO = os.path.join(HERE, "_ref", "libsks_ref.so")
 REF_O3_SO = os.path.join(HERE, "_ref", "libsks_ref_o3.so")
 REFGPU_SO = os.path.join(HERE, "_ref", "libsks_refgpu.so")
 REFGPU_NOFMA_SO = os.path.join(HERE, "_ref", "libsks_refgpu_nofma.so")
+REF_TORCH_PY = os.path.join(HERE, "_ref", "ref_torch_funcs.py")     # staged by oracle/stage_ref.py
+REF_FIXTURE = os.path.join(HERE, "_ref", "orig_pts_wall.txt")         # CPU/orig_pts_wall.txt, staged likewise
 REFERENCE_ROOT = "/root/reference"
 
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference checkout exists)."""
     need = force or not os.path.exists(ORACLE_SO)
-    if os.path.isdir(REFERENCE_ROOT) and not all(os.path.exists(f) for f in (REF_SO, REF_O3_SO, REFGPU_SO, REFGPU_NOFMA_SO)):
+    if os.path.isdir(REFERENCE_ROOT) and not all(os.path.exists(f) for f in (
+            REF_SO, REF_O3_SO, REFGPU_SO, REFGPU_NOFMA_SO, REF_TORCH_PY, REF_FIXTURE)):
         need = True
     if need:
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True,
@@ -223,3 +226,16 @@ class RefGpuLib:
         rc = getattr(self.lib, f"refgpu_{solver}_f64")(d_src, d_tar, d_H, n, stream)
         if rc != 0:
             raise RuntimeError(f"reference CUDA kernel launch failed: cudaError {rc}")
+
+
+def ref_torch_funcs():
+    """The reference's own torch statements (PY.py getInput / getTar / adjust, the timed bodies of
+    TensorACA_rect :296-302 and ACA_vanilla :322-381), staged into oracle/_ref at build time.
+    Returns the module, or raises FileNotFoundError where it was never staged."""
+    import importlib.util
+    if not os.path.exists(REF_TORCH_PY):
+        raise FileNotFoundError(f"{REF_TORCH_PY} not staged (run `make -C oracle stage` where /root/reference exists)")
+    spec = importlib.util.spec_from_file_location("ref_torch_funcs", REF_TORCH_PY)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

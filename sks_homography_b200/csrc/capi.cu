@@ -440,13 +440,30 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
 #undef SKS_RANSAC_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    // chunk: enough hypotheses per CTA to amortise the tile load, enough CTAs
-    // to fill the machine several times over
+    // chunk = rounds * (threads * hpt) hypothesis ids per CTA.  CTAs of one launch all take the
+    // same time, so the launch runs in ceil(CTAs / resident slots) waves: 1024 pairs x 2 chunks on
+    // 444 slots is 4.6 waves of work but 5 waves of time (8 % lost at 8 ranks, measured 13.0 ms =
+    // 5 x 2.6 ms).  Pick the rounds per CTA -- the tuning value, halved down to 1 -- that
+    // minimises waves x (rounds + fixed cost), the fixed cost being the tile load and re-layout
+    // (~10 us against ~330 us per round at 4096 matches, i.e. ~0.03 rounds).
     const uint32_t round = (uint32_t)threads * (uint32_t)hpt;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    const double slots = (double)dev.sms * occ;
     uint32_t chunk = round * (uint32_t)g_ransac_rounds.load();
-    while (chunk > round &&
-           (int64_t)((hyp_count + chunk - 1) / chunk) * n_pairs < (int64_t)dev.sms * 8)
-        chunk -= round;
+    double best_cost = 0;
+    for (uint32_t r = (uint32_t)g_ransac_rounds.load(), first = 1; r >= 1; r /= 2, first = 0) {
+        const double ctas = (double)((hyp_count + r * round - 1) / (r * round)) * (double)n_pairs;
+        const double waves = (double)(int64_t)((ctas + slots - 1) / slots);
+        const double cost = (waves < 1 ? 1 : waves) * ((double)r + 0.03);
+        if (first || cost < best_cost * 0.995) {     // prefer more rounds per CTA unless it pays clearly
+            best_cost = cost;
+            chunk = r * round;
+        }
+        if (r == 1) break;
+    }
     const unsigned chunks = (hyp_count + chunk - 1) / chunk;
     // grid.y is limited to 65535: larger batches go out in blocks of pairs; the kernel
     // takes its pair id from pair_base + blockIdx.y so sampling does not depend on blocking

@@ -305,3 +305,39 @@ def test_score_given_models_and_polish(api, oracle, cuda):
                 mc[p] = api.ransac_score(corr[p:p + 1], torch.from_numpy(H2[p:p + 1]).to(cuda), 2.25)[1][0].cpu().numpy()
     assert np.array_equal(Hp.cpu().numpy().view(np.uint32), Hc.view(np.uint32))
     assert np.array_equal(cp.cpu().numpy().astype(np.int64), cc)
+
+
+def test_real_matches_fixture_gather_ransac_refit(api, oracle, cuda):
+    """The reference's real-data fixture (2540 wall matches, CPU/orig_pts_wall.txt, staged into the
+    git-ignored oracle/_ref at build time): minimal-sample gather -> solve replays the reference's GPU
+    flow (GPU.cu:1443-1464) on real matches, the fused RANSAC finds the wall's homography with the
+    oracle's exact keys (~63 % of the matches at 3 px), and the refit keeps it."""
+    import os
+    from oracle.oracle import REF_FIXTURE
+    from sks_homography_b200.io import read_points
+    if not os.path.exists(REF_FIXTURE):
+        pytest.skip("fixture not staged (oracle/_ref/orig_pts_wall.txt; run `make -C oracle stage`)")
+    pool_np = read_points(REF_FIXTURE)
+    assert pool_np.shape == (2540, 4)
+    corr = torch.from_numpy(pool_np)[None].contiguous().to(cuda)
+    n_hyp, seed, thr2 = 4096, 11, 9.0
+    keys = api.ransac_keys(corr, n_hyp, seed, thr2)
+    want = oracle.ransac(pool_np[None], n_hyp, seed, thr2)
+    assert np.array_equal(u64(keys), want)
+    H, cnt, mask = api.ransac_finalize(corr, n_hyp, seed, thr2, keys, want_mask=True)
+    frac = int(cnt[0]) / 2540
+    assert 0.55 < frac < 0.70 and int(mask.sum()) == int(cnt[0])
+    H2, used = api.ransac_refit(corr, mask, H)
+    cnt2, _ = api.ransac_score(corr, H2, thr2)
+    assert int(used[0]) == int(cnt[0]) and int(cnt2[0]) >= 0.97 * int(cnt[0])
+    # hypothesis generation from the pool with the reference's cuRAND sample list (seed 11, GPU.cu:1445)
+    n = 8192
+    rand4 = api.curand_mrg32k3a(4 * n, seed=11, device=cuda).view(4, n)
+    Hg = api.gather_solve("aca", corr[0].double(), n, rand4=rand4)
+    idx = (rand4.cpu().numpy().view(np.uint32) % 2540).T                     # [n, 4]
+    sel = pool_np.astype(np.float64)[idx]                                    # [n, 4, 4]
+    src, tar = sel[:, :, :2].reshape(n, 8), sel[:, :, 2:].reshape(n, 8)
+    wantH = oracle.solve("aca", src, tar)
+    got = Hg.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(wantH))
+    assert np.array_equal(np.nan_to_num(got).view(np.uint64), np.nan_to_num(wantH).view(np.uint64))

@@ -32,6 +32,12 @@ WANT = [
     "launch__waves_per_multiprocessor", "launch__occupancy_limit_shared_mem",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_warps",
     "sm__maximum_warps_per_active_cycle_pct", "smsp__cycles_active.avg",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
 ]
 
 
