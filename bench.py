@@ -327,6 +327,24 @@ class Ctx:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def host_wait_for_rank0(self, tag: str, work=None):
+        """Rank 0 runs `work()` while the other ranks block on the HOST (the rendezvous store), so that
+        their GPUs are idle -- an NCCL barrier would park a spinning kernel on every waiting GPU."""
+        self.barrier()
+        out = None
+        if self.world == 1:
+            return work() if work else None
+        store = self.dist.distributed_c10d._get_default_store()
+        if self.rank == 0:
+            try:
+                out = work() if work else None
+            finally:
+                store.set(tag, "done")
+        else:
+            store.wait([tag])
+        self.barrier()
+        return out
+
     def max_over_ranks(self, x: float) -> float:
         t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
         if self.world > 1:
@@ -863,9 +881,8 @@ def measure_ransac_inprocess(cx, steps=5):
     rank 0 alone drives `world` GPUs -- matches on its own device, the others read them over NVLink peer
     access and merge their winners with peer atomics -- while the other ranks wait at a barrier."""
     torch, api, args = cx.torch, cx.api, cx.args
-    out = None
-    cx.barrier()
-    if cx.rank == 0:
+
+    def work():
         try:
             ngpu = min(cx.world, torch.cuda.device_count())
             P, n_pts, n_hyp, thr2 = args.pairs, args.points, args.hyps, 2.25
@@ -884,16 +901,16 @@ def measure_ransac_inprocess(cx, steps=5):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            out = {"api": "sks_cuda_ransac_aca_multi_f32 (one process, one enqueueing thread, NVLink peer reads + "
-                          "peer atomics, CUDA-event ordering; no NCCL, no IPC)", "gpus": ngpu, "steps": steps,
-                   "ms_per_step": ms, "value": P * n_hyp / (ms * 1e-3), "unit": "hypotheses/s",
-                   "bit_identical_to_one_gpu": bool(torch.equal(kn, k1) and torch.equal(cn, c1) and
-                                                    torch.equal(Hn.view(torch.int32), H1.view(torch.int32)))}
-            del corr
+            return {"api": "sks_cuda_ransac_aca_multi_f32 (one process, one enqueueing thread, NVLink peer reads + "
+                           "peer atomics, CUDA-event ordering; no NCCL, no IPC)", "gpus": ngpu, "steps": steps,
+                    "ms_per_step": ms, "value": P * n_hyp / (ms * 1e-3), "unit": "hypotheses/s",
+                    "other_ranks": "blocked on the host (rendezvous store), GPUs idle",
+                    "bit_identical_to_one_gpu": bool(torch.equal(kn, k1) and torch.equal(cn, c1) and
+                                                     torch.equal(Hn.view(torch.int32), H1.view(torch.int32)))}
         except Exception as e:
-            out = {"error": f"{type(e).__name__}: {e}"[:200]}
-    cx.barrier()
-    return out
+            return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+    return cx.host_wait_for_rank0("ransac_inprocess_multi_done", work)
 
 
 def accuracy_tier_f64(cx, m, src, tar, H):

@@ -255,9 +255,10 @@ int sks_cuda_ransac_finalize_f32(const float *corr, int64_t n_pairs, int32_t n_p
  * callers that are ONE process, not one process per GPU: the whole estimate -- zero the keys,
  * score hypothesis ids [0, n_hyp) of every pair, merge, rebuild the winners -- over `ngpu`
  * devices (the current one, which owns corr / samples and all outputs, plus the next ngpu-1 in
- * index order; 0 = all visible).  Device k scores the k-th contiguous shard of the hypothesis
- * ids, reading the matches straight from the current device's memory over NVLink peer access
- * (nothing is replicated), and max-combines its winners into best_key with system-scope
+ * index order; 0 = all visible).  The matches reach the other devices by a binomial-tree
+ * broadcast of NVLink peer copies into library-owned buffers (an explicit sample list is read
+ * in place over peer access); device k scores the k-th contiguous shard of the hypothesis ids
+ * as soon as its copy has landed and max-combines its winners into best_key with system-scope
  * atomics; CUDA events order the devices' streams, so the call only enqueues, like every other
  * sks_cuda_* entry: results are valid when `stream` reaches the end of the enqueued work.  No
  * NCCL, no IPC.  best_key [n_pairs] is overwritten (not max-combined).  H_best may be NULL to

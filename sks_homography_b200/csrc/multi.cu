@@ -2,18 +2,22 @@
 // entry sks_cuda_*_multi(..., int ngpu)", 8(e) variant A): ONE process, ONE enqueueing host
 // thread, no NCCL and no CUDA IPC.  The hypothesis ids of every image pair are cut into ngpu
 // contiguous shards; device k scores its shard with the unmodified fused kernel
-// (sks_cuda_ransac_aca_shard_f32), reading the correspondences
-// straight out of the primary device's memory over NVLink peer access -- the tile bulk copies
-// (TMA) and the 4-match sample gathers of k_ransac_aca simply take peer addresses, so the
-// transfer is part of the scoring kernel, tile by tile, and nothing is replicated beforehand
-// (the host-pointer entry copies the matches to the primary once, over one PCIe link: eight
-// H2D copies of the same 64 MiB would only contend for the host's memory system) --
-// and max-combines its per-pair winners into the primary device's key array with
-// system-scope atomicMax over NVLink (k_multi_push_max, 8 KiB for 1024 pairs).  Ordering is
-// all CUDA events between the devices' streams: peers start after the caller's stream has
-// reached the call, the primary's finalize starts after every peer's push.  The primary then
-// rebuilds the winners from their ids -- no homography travels.  Bit-identical to one GPU by
-// construction (integer max of the same keys).
+// (sks_cuda_ransac_aca_shard_f32) and max-combines its per-pair winners into the primary
+// device's key array with system-scope atomicMax over NVLink (k_multi_push_max, 8 KiB for 1024
+// pairs).  The correspondences reach the peers by a binomial-tree broadcast of peer copies
+// over NVLink (device 0 -> 1, then 0 -> 2 and 1 -> 3, then 0..3 -> 4..7: log2(ngpu) stages of
+// 64 MiB at ~0.09 ms each, every device starting to score as soon as its copy has landed; the
+// host-pointer entry copies the matches to the primary once, over one PCIe link -- eight H2D
+// copies of the same 64 MiB would only contend for the host's memory system).  Reading them in
+// place over peer access instead (the tile bulk copies and sample gathers of k_ransac_aca accept
+// peer addresses, and tests/test_gpu_multi.py ran that way at 2 GPUs) makes every CTA re-fetch
+// its pair's 64 KiB tile from the primary: at 8 GPUs with 16 chunks per pair that is 7 GiB of
+// NVLink egress from one device per step, 20.2 ms against 12.2 ms (profiles/r02_bench_n8.json),
+// so only an explicit sample list -- 16 B per hypothesis, read once -- is still read in place.
+// Ordering is all CUDA events between the devices' streams: copies start after the caller's
+// stream has reached the call, the primary's finalize starts after every peer's push.  The
+// primary then rebuilds the winners from their ids -- no homography travels.  Bit-identical to
+// one GPU by construction (integer max of the same keys).
 #include <cstdint>
 #include <mutex>
 #include <vector>
@@ -46,8 +50,11 @@ struct PeerDev {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t copied = nullptr;         // this device's copy of the matches has landed
     unsigned long long* keys = nullptr;   // this device's per-pair winners
     size_t keys_cap = 0;
+    float* corr = nullptr;                // this device's copy of the matches
+    size_t corr_cap = 0;
 };
 
 struct MultiCtx {
@@ -113,8 +120,23 @@ int get_ctx(int primary, int ngpu, int visible, MultiCtx** out)
         }
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.copied, cudaEventDisableTiming);
+        // broadcast tree: peer index k = peers.size() + 1 pulls from k - 2^floor(log2 k)
+        const int k = (int)c->peers.size() + 1;
+        int top = 1;
+        while (top * 2 <= k) top *= 2;
+        const int parent = k - top;
+        if (e == cudaSuccess && parent > 0) {
+            e = cudaDeviceEnablePeerAccess(c->peers[parent - 1].device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                e = cudaSuccess;
+            }
+        }
         if (e != cudaSuccess) {
             if (p.stream) cudaStreamDestroy(p.stream);
+            if (p.done) cudaEventDestroy(p.done);
+            if (p.copied) cudaEventDestroy(p.copied);
             cudaSetDevice(primary);
             return (int)e;
         }
@@ -133,10 +155,33 @@ int enqueue_sharded(MultiCtx* c, int ngpu, const float* corr, const uint32_t* sa
                     cudaStream_t st)
 {
     const size_t key_bytes = (size_t)n_pairs * sizeof(unsigned long long);
+    const size_t corr_bytes = (size_t)n_pairs * n_pts * 4 * sizeof(float);
     CK(cudaSetDevice(c->primary));
     CK(cudaMemsetAsync(best_key, 0, key_bytes, st));
     CK(cudaEventRecord(c->ready, st));       // inputs valid and keys zeroed from here on
     int rc = SKS_OK;
+    // binomial-tree broadcast of the matches: peer k pulls from k - 2^floor(log2 k) on its own
+    // stream, after the source holds the data AND has finished its previous send (so that a
+    // source's NVLink egress serves one child at a time: log2(ngpu) stages in all)
+    std::vector<cudaEvent_t> last_send(ngpu, nullptr);
+    for (int k = 1; k < ngpu && rc == SKS_OK; ++k) {
+        PeerDev& p = c->peers[k - 1];
+        int top = 1;
+        while (top * 2 <= k) top *= 2;
+        const int parent = k - top;
+        const float* src = parent == 0 ? corr : c->peers[parent - 1].corr;
+        const int src_dev = parent == 0 ? c->primary : c->peers[parent - 1].device;
+        if ((rc = (int)cudaSetDevice(p.device)) != SKS_OK) break;
+        if ((rc = grow(reinterpret_cast<void**>(&p.corr), &p.corr_cap, corr_bytes)) != SKS_OK) break;
+        if ((rc = (int)cudaStreamWaitEvent(p.stream, parent == 0 ? c->ready : c->peers[parent - 1].copied, 0)) != SKS_OK)
+            break;
+        if (last_send[parent] != nullptr &&
+            (rc = (int)cudaStreamWaitEvent(p.stream, last_send[parent], 0)) != SKS_OK)
+            break;
+        if ((rc = (int)cudaMemcpyPeerAsync(p.corr, p.device, src, src_dev, corr_bytes, p.stream)) != SKS_OK) break;
+        if ((rc = (int)cudaEventRecord(p.copied, p.stream)) != SKS_OK) break;
+        last_send[parent] = p.copied;
+    }
     for (int k = 1; k < ngpu && rc == SKS_OK; ++k) {
         PeerDev& p = c->peers[k - 1];
         int64_t hb = 0, hc = 0;
@@ -145,7 +190,7 @@ int enqueue_sharded(MultiCtx* c, int ngpu, const float* corr, const uint32_t* sa
         if ((rc = grow(reinterpret_cast<void**>(&p.keys), &p.keys_cap, key_bytes)) != SKS_OK) break;
         if ((rc = (int)cudaStreamWaitEvent(p.stream, c->ready, 0)) != SKS_OK) break;
         if ((rc = (int)cudaMemsetAsync(p.keys, 0, key_bytes, p.stream)) != SKS_OK) break;
-        rc = sks_cuda_ransac_aca_shard_f32(corr, 0, n_pairs, n_pts, samples, n_hyp, (uint32_t)hb,
+        rc = sks_cuda_ransac_aca_shard_f32(p.corr, 0, n_pairs, n_pts, samples, n_hyp, (uint32_t)hb,
                                            (uint32_t)hc, seed, thr2, p.keys, p.stream);
         if (rc != SKS_OK) break;
         k_multi_push_max<<<(unsigned)((n_pairs + 255) / 256), 256, 0, p.stream>>>(p.keys, best_key, n_pairs);
@@ -281,7 +326,9 @@ void sks_multi_shutdown_internal(void)
             cudaSetDevice(p.device);
             if (p.stream) { cudaStreamSynchronize(p.stream); cudaStreamDestroy(p.stream); }
             if (p.done) cudaEventDestroy(p.done);
+            if (p.copied) cudaEventDestroy(p.copied);
             if (p.keys) cudaFree(p.keys);
+            if (p.corr) cudaFree(p.corr);
         }
         cudaSetDevice(c->primary);
         if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }

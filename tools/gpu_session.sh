@@ -16,6 +16,9 @@ case "$stage" in
   ncu_ransac)   for cfg in "3 2" "3 4" "1 2"; do set -- $cfg; timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_ransac_aca -s 1 -c 1 -f -o gpurun_out/ransac_m$1_h$2 python tools/ransac_once.py 444 $1 $2 > gpurun_out/ncu_ransac_m$1_h$2.log 2>&1; tail -2 gpurun_out/ncu_ransac_m$1_h$2.log; done ;;
   multi_tests)  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x --timeout 300 2>&1 | tail -15 | tee gpurun_out/multi_tests.log ;;
   cpp_multi)    g++ -std=c++17 -O2 -I include tests/cpp/ransac_multi_main.cpp -o /tmp/ransac_multi -L sks_homography_b200 -lsks_cuda -Wl,-rpath,$PWD/sks_homography_b200 && timeout 300 /tmp/ransac_multi 1024 4096 65536 2>&1 | tee gpurun_out/cpp_multi.log ;;
+  bench_n)      N=${NGPU:-2}; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -c 1500 gpurun_out/bench_n$N.json; grep "\[bench\]" gpurun_out/bench_n$N.err ;;
+  launch_list)  timeout 600 python bench.py --steps 20 --warmup 5 --sustained-s 0 > gpurun_out/plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 20 --warmup 5 --sustained-s 0 > gpurun_out/ncu_launch.log 2>&1; tail -3 gpurun_out/ncu_launch.log; wc -l gpurun_out/launches_bench.csv ;;
+  pcie_multi)   N=${NGPU:-2}; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29556 tools/pcie_multi_probe.py 2> gpurun_out/pcie_multi_n$N.err | tee gpurun_out/pcie_multi_probe_n$N.log; tail -3 gpurun_out/pcie_multi_n$N.err ;;
   *) echo "unknown stage $stage" ;;
 esac
 done
