@@ -350,7 +350,8 @@ void sks_cuda_reset_launch_count(void);
 /* Kernel variant for the AoS streaming solvers: 0 = default (best measured, = 1),
  * 1 = direct vector loads + shared-memory transposed stores,
  * 2 = persistent TMA bulk-copy ring (cp.async.bulk + mbarrier); 2 also keeps the fused
- * gather+solve entry points on their L1 gather path instead of the shared-memory-pool kernel.
+ * gather+solve entry points on their L1 gather path instead of the shared-memory-pool kernel;
+ * 3 = warp-private TMA ring (every warp its own producer, no CTA-wide barrier).
  * A tuning knob for bench.py sweeps and tests, not a backend switch: every variant is
  * sm_100a CUDA. */
 int sks_cuda_set_variant(int variant);

@@ -23,7 +23,7 @@ using namespace sksb;
 namespace {
 
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_variant{0};        // 0 default, 1 direct, 2 ring
+std::atomic<int> g_variant{0};        // 0 default, 1 direct, 2 ring, 3 warp-private ring
 std::atomic<int> g_tile_small{0};     // ring tile: 0 = 256/128 (f32/f64), 1 = 128/64
 std::atomic<int> g_stages{4};
 std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
@@ -97,6 +97,38 @@ int launch_ring(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, 
     return finish_launch();
 }
 
+// variant 3: warp-private TMA ring.  Shapes measured on B200 (tools/wring_sweep.py,
+// profiles/r02_wring_sweep.log; QPW quadruples per warp tile x stages x warps per CTA):
+// fp32 64 x 2 x 16 (ACA 5.87 TB/s, rect 6.37), fp64 32 x 3 x 8 (SKS 6.57 TB/s) -- all bit-exact,
+// all below the direct kernel's 7.0 TB/s, which therefore stays the default.
+template <int SOLVER, typename T>
+int launch_wring(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, uint8_t* degen,
+                 int64_t n, bool normalize, const DevInfo& dev, cudaStream_t st)
+{
+#ifdef SKS_WRING_QPW_F32      // sweep builds: one shape for both precisions
+    constexpr int QPW = sizeof(T) == 4 ? SKS_WRING_QPW_F32 : (SKS_WRING_QPW_F32 >= 64 ? SKS_WRING_QPW_F32 / 2 : 32),
+                  STAGES = SKS_WRING_STAGES, WARPS = SKS_WRING_WARPS;
+#else
+    constexpr int QPW = sizeof(T) == 4 ? 64 : 32, STAGES = sizeof(T) == 4 ? 2 : 3, WARPS = sizeof(T) == 4 ? 16 : 8;
+#endif
+    using L = WringLayout<SOLVER, T, QPW, STAGES>;
+    auto kern = k_aos_wring<SOLVER, T, WARPS, QPW, STAGES>;
+    const int smem = L::smem_bytes(WARPS);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    const int want = g_ctas_per_sm.load();
+    if (want > 0 && want < occ) occ = want;
+    const int64_t n_tiles = (n + QPW - 1) / QPW;
+    const int64_t ctas_needed = (n_tiles + WARPS - 1) / WARPS;
+    const int64_t grid = ctas_needed < (int64_t)dev.sms * occ ? ctas_needed : (int64_t)dev.sms * occ;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(src, tar, M, rp, H, degen, n, normalize);
+    return finish_launch();
+}
+
 template <int SOLVER, typename T>
 int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, int64_t n,
                   int layout, int64_t ld, int flags, uint8_t* degen, void* stream)
@@ -150,6 +182,12 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
             k_aos_direct<SOLVER, T, BIG, false><<<(unsigned)grid, BIG, 0, st>>>(src, tar, M, rp, H,
                                                                                 degen, n, normalize);
         return finish_launch();
+    }
+    if (variant == 3) {
+        if constexpr (SOLVER == SOLVER_GPT)        // 200 registers: stays on the direct kernel
+            return SKS_ERR_INVALID_ARG;
+        else
+            return launch_wring<SOLVER, T>(src, tar, M, rp, H, degen, n, normalize, dev, st);
     }
     if (g_tile_small.load())
         return launch_ring<SOLVER, T, SMALL>(src, tar, M, rp, H, degen, n, normalize, dev, st);
@@ -651,7 +689,7 @@ void sks_cuda_reset_launch_count(void) { g_launches.store(0); }
 
 int sks_cuda_set_variant(int variant)
 {
-    if (variant < 0 || variant > 2) return SKS_ERR_INVALID_ARG;
+    if (variant < 0 || variant > 3) return SKS_ERR_INVALID_ARG;
     g_variant.store(variant);
     return SKS_OK;
 }

@@ -1,6 +1,6 @@
 // Streaming solver kernels: one thread per correspondence quadruple, HBM-bound
 // (arithmetic intensity ~1 flop/B, >10x below the B200 ridge, so no tensor
-// cores: there is no contraction to feed them).  Three kernels per
+// cores: there is no contraction to feed them).  Four kernels per
 // (solver, precision):
 //
 //   k_aos_ring    persistent CTAs; the AoS input tiles are pulled into a
@@ -10,6 +10,8 @@
 //                 shared loads, and the 9-word results are transposed through
 //                 shared memory and leave as one bulk shared->global copy per
 //                 tile.  No register-staged global traffic at all.
+//   k_aos_wring   the same with a PRIVATE ring per warp: lane 0 of every warp is its
+//                 own TMA producer, so the kernel has no CTA-wide barrier at all.
 //   k_aos_direct  one tile per CTA; each thread pulls its own quadruple with
 //                 256-bit loads (sm_100's LDG.256: one full 32-byte sector per
 //                 lane) or, for pointers that are only 16-byte aligned, 16-byte
@@ -531,6 +533,143 @@ k_aos_ring(const T* __restrict__ src, const T* __restrict__ tar, const T* __rest
         }
     }
     if (tid == 0)
+        bulk_wait_all<0>();
+}
+
+// -------------------------------------------------------------- k_aos_wring
+// Warp-private TMA ring (variant 3): the k_aos_ring idea without a single CTA-wide barrier.
+// Every WARP of a persistent CTA owns a private multi-stage ring in shared memory, its own
+// `full` mbarriers and two private output buffers, and walks tiles of QPW quadruples
+// (tile t belongs to global warp t mod G).  Lane 0 is the warp's producer: it arms a stage's
+// barrier and hands the tile's AoS bytes to the bulk-copy (TMA) engine; once the warp has read
+// a stage (a __syncwarp away) the same lane refills it, so no `empty` barrier and no producer
+// warp are needed and the copy engine always has STAGES tiles per warp in flight.  Results are
+// staged at stride 9 words and leave as one bulk shared->global copy per tile (double-buffered
+// on the bulk async-group of lane 0).
+template <int SOLVER, typename T, int QPW, int STAGES>
+struct WringLayout {
+    static constexpr int NARR = (SOLVER == SOLVER_RECT) ? 1 : 2;
+    static constexpr int ARR_BYTES = QPW * 8 * (int)sizeof(T);
+    static constexpr int STAGE_BYTES = ARR_BYTES * NARR;
+    static constexpr int OUT_BYTES = QPW * 9 * (int)sizeof(T);
+    static constexpr int OUT_PAD = (OUT_BYTES + 127) & ~127;
+    static constexpr int WARP_BYTES = STAGES * STAGE_BYTES + 2 * OUT_PAD + 128;   // + barriers
+    static __host__ __device__ constexpr int smem_bytes(int warps) { return warps * WARP_BYTES; }
+};
+
+template <int SOLVER, typename T, int WARPS, int QPW, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32)
+k_aos_wring(const T* __restrict__ src, const T* __restrict__ tar, const T* __restrict__ M,
+            RectParams<T> rp, T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, bool normalize)
+{
+    using L = WringLayout<SOLVER, T, QPW, STAGES>;
+    static_assert(QPW % 32 == 0, "whole quadruples per lane");
+    constexpr int PER_LANE = QPW / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = smem + (size_t)warp * L::WARP_BYTES;
+    unsigned char* ring = mine;
+    unsigned char* outs = mine + STAGES * L::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(outs + 2 * L::OUT_PAD);
+
+    const int64_t n_tiles = (n + QPW - 1) / QPW;
+    const int64_t G = (int64_t)gridDim.x * WARPS;
+    const int64_t first = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t my_tiles = first < n_tiles ? (n_tiles - first + G - 1) / G : 0;
+
+    auto issue = [&](int64_t it, int s) {       // lane 0 only
+        const int64_t q0 = (first + it * G) * QPW;
+        const int64_t left = n - q0;
+        const uint32_t cnt = (uint32_t)(left < (int64_t)QPW ? left : (int64_t)QPW);
+        const uint32_t bytes = cnt * 8u * (uint32_t)sizeof(T);
+        unsigned char* dst = ring + s * L::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], bytes * L::NARR);
+        if constexpr (SOLVER != SOLVER_RECT) {
+            bulk_g2s(dst, src + q0 * 8, bytes, &full[s]);
+            bulk_g2s(dst + L::ARR_BYTES, tar + q0 * 8, bytes, &full[s]);
+        } else {
+            bulk_g2s(dst, tar + q0 * 8, bytes, &full[s]);
+        }
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s)
+            mbar_init(&full[s], 1);
+        mbar_init_fence();
+        for (int s = 0; s < STAGES && s < my_tiles; ++s)
+            issue(s, s);
+    }
+    __syncwarp();
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t q0 = (first + it * G) * QPW;
+        const int64_t left = n - q0;
+        const int cnt = (int)(left < (int64_t)QPW ? left : (int64_t)QPW);
+        mbar_wait(&full[s], parity);            // this stage's bytes have landed
+        T sv[PER_LANE][8], tv[PER_LANE][8];
+        const unsigned char* st = ring + s * L::STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+            const int q = lane + 32 * j;
+            if (q < cnt) {
+                if constexpr (SOLVER != SOLVER_RECT) {
+                    load_quad_smem<T>(st, q, sv[j]);
+                    load_quad_smem<T>(st + L::ARR_BYTES, q, tv[j]);
+                } else {
+                    load_quad_smem<T>(st, q, tv[j]);
+                }
+            }
+        }
+        // the output buffer about to be overwritten was handed to the copy engine two tiles ago
+        if (lane == 0)
+            bulk_wait_read<1>();
+        __syncwarp();                            // stage s fully read by the warp, out[it&1] free
+        if (lane == 0 && it + STAGES < my_tiles) {
+            fence_async_smem();                  // generic-proxy reads of the stage precede its refill
+            issue(it + STAGES, s);
+        }
+        T* out = reinterpret_cast<T*>(outs + (size_t)(it & 1) * L::OUT_PAD);
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+            const int q = lane + 32 * j;
+            if (q < cnt) {
+                const int64_t i = q0 + q;
+                T mx = rp.mx, my = rp.my;
+                if constexpr (SOLVER == SOLVER_RECT)
+                    if (M != nullptr)
+                        load_corner_aos<T>(M, i, mx, my);
+                T h[9];
+                solve_quad<SOLVER, T>(sv[j], tv[j], mx, my, rp, h, normalize);
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    out[q * 9 + k] = h[k];       // stride 9 words: conflict-free
+                if (degen != nullptr)
+                    degen[i] = is_degenerate<T>(h, normalize) ? 1 : 0;
+            }
+        }
+        fence_async_smem();                      // results visible to the async proxy
+        __syncwarp();
+        const uint32_t out_bytes = (uint32_t)cnt * 9u * (uint32_t)sizeof(T);
+        if ((out_bytes & 15u) == 0) {
+            if (lane == 0) {
+                bulk_s2g(H + q0 * 9, out, out_bytes);
+                bulk_commit();
+            }
+        } else {                                 // ragged last tile: not a 16-byte multiple
+            for (int e = lane; e < cnt * 9; e += 32)
+                H[q0 * 9 + e] = out[e];
+            if (lane == 0)
+                bulk_commit();                   // empty group keeps the one-group-per-tile count
+            __syncwarp();
+        }
+        if (++s == STAGES) {
+            s = 0;
+            parity ^= 1;
+        }
+    }
+    if (lane == 0)
         bulk_wait_all<0>();
 }
 

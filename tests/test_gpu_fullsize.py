@@ -45,6 +45,10 @@ def test_config2_aca_f32_2pow26(api, sks, oracle, cuda):
     H2 = api.solve("aca", src, tar)
     assert torch.equal(H1.view(torch.int32), H2.view(torch.int32))
     del H2
+    sks.c.sks_cuda_set_variant(3)          # warp-private TMA ring
+    H3 = api.solve("aca", src, tar)
+    assert torch.equal(H1.view(torch.int32), H3.view(torch.int32))
+    del H3
     # every h33 is exactly 1, every quadruple of this distribution is well posed
     assert bool((H1[:, 8] == 1.0).all()) and bool(torch.isfinite(H1).all())
     # linearity-free but cheap global property: SKS agrees with ACA to fp32 conditioning

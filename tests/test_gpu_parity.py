@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 TDT = {np.float32: torch.float32, np.float64: torch.float64}
 VARIANTS = {"direct": (1, 0, 4, 0), "direct_16B": (1, 2, 4, 0), "ring": (2, 0, 4, 0),
-            "ring_small_3": (2, 1, 3, 0), "ring_1cta_2": (2, 0, 2, 1)}
+            "ring_small_3": (2, 1, 3, 0), "ring_1cta_2": (2, 0, 2, 1), "wring": (3, 0, 4, 0)}
 
 
 @pytest.fixture
@@ -51,8 +51,8 @@ def test_aos_bit_exact(api, sks, oracle, cuda, solver, dtype, variant):
         assert np.array_equal(flag.cpu().numpy(), oracle.degenerate(want, normalize))
 
 
-@pytest.mark.parametrize("variant", ["direct", "direct_16B", "ring"])
-@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 31, 255, 256, 257, 511, 1000, 4099])
+@pytest.mark.parametrize("variant", ["direct", "direct_16B", "ring", "wring"])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 31, 63, 64, 65, 255, 256, 257, 511, 1000, 4099])
 def test_ragged_sizes(api, sks, oracle, cuda, n, variant):
     set_variant(sks, variant)
     for dtype in (np.float32, np.float64):
@@ -79,7 +79,7 @@ def test_soa_bit_exact(api, oracle, cuda, solver, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("variant", ["direct", "direct_16B", "ring"])
+@pytest.mark.parametrize("variant", ["direct", "direct_16B", "ring", "wring"])
 def test_ge_competitor_bit_exact(api, sks, oracle, golden, cuda, dtype, variant):
     """RHO-GE (MOD/GE.cpp) through the same streaming kernels:
     AoS and SoA, ragged sizes, the reference's golden vectors, host-pointer path."""
@@ -177,7 +177,7 @@ def test_degenerate_flags_identical(api, oracle, golden, cuda):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("variant", ["direct", "ring"])
+@pytest.mark.parametrize("variant", ["direct", "ring", "wring"])
 def test_aca_rect_bit_exact(api, sks, oracle, cuda, dtype, variant):
     set_variant(sks, variant)
     n = (1 << 19) + 5

@@ -19,6 +19,8 @@ case "$stage" in
   bench_n)      N=${NGPU:-2}; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -c 1500 gpurun_out/bench_n$N.json; grep "\[bench\]" gpurun_out/bench_n$N.err ;;
   launch_list)  timeout 600 python bench.py --steps 20 --warmup 5 --sustained-s 0 > gpurun_out/plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 20 --warmup 5 --sustained-s 0 > gpurun_out/ncu_launch.log 2>&1; tail -3 gpurun_out/ncu_launch.log; wc -l gpurun_out/launches_bench.csv ;;
   pcie_multi)   N=${NGPU:-2}; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29556 tools/pcie_multi_probe.py 2> gpurun_out/pcie_multi_n$N.err | tee gpurun_out/pcie_multi_probe_n$N.log; tail -3 gpurun_out/pcie_multi_n$N.err ;;
+  wring_sweep)  timeout 900 python tools/wring_sweep.py 2>&1 | tee gpurun_out/wring_sweep.log ;;
+  parity_tests) timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 2>&1 | tail -5 | tee gpurun_out/parity_tests.log ;;
   *) echo "unknown stage $stage" ;;
 esac
 done
