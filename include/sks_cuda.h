@@ -117,6 +117,16 @@ int sks_cuda_aca_rect_planar_f32(const float *tar34, const float *src34, float m
 int sks_cuda_aca_rect_planar_f64(const double *tar34, const double *src34, double mx, double my,
                                  double width, double ratio, double *H, int64_t n, int flags,
                                  uint8_t *degenerate, void *stream);
+/* The same with the rectangle's width (`scale`) and width/height ratio (`div`) read from
+ * one-element DEVICE arrays, as the reference holds them (PY.py:33-35: tensors derived from
+ * batch element 0, used at :301-302): no device->host synchronisation to fetch two scalars.
+ * src34 supplies the per-sample corner as above (NULL: corner (0, 0)). */
+int sks_cuda_aca_rect_planar_dev_f32(const float *tar34, const float *src34, const float *width_dev,
+                                     const float *ratio_dev, float *H, int64_t n, int flags,
+                                     uint8_t *degenerate, void *stream);
+int sks_cuda_aca_rect_planar_dev_f64(const double *tar34, const double *src34,
+                                     const double *width_dev, const double *ratio_dev, double *H,
+                                     int64_t n, int flags, uint8_t *degenerate, void *stream);
 
 /* ---- host-pointer entry points (what the reference's C++ callers hold) ---- */
 /* Drop-in for the loop `for (k...) sks::runKernel_*(src, tar, result)` of

@@ -52,6 +52,8 @@ _SIGS = {
     "sks_cuda_aca_rect_f64": (_int, [_vp, _vp, _f64, _f64, _f64, _f64, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "sks_cuda_aca_rect_planar_f32": (_int, [_vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _int, _vp, _vp]),
     "sks_cuda_aca_rect_planar_f64": (_int, [_vp, _vp, _f64, _f64, _f64, _f64, _vp, _i64, _int, _vp, _vp]),
+    "sks_cuda_aca_rect_planar_dev_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "sks_cuda_aca_rect_planar_dev_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "sks_host_aca_f32": (_int, [_vp, _vp, _vp, _i64, _int]),
     "sks_host_aca_f64": (_int, [_vp, _vp, _vp, _i64, _int]),
     "sks_host_sks_f32": (_int, [_vp, _vp, _vp, _i64, _int]),

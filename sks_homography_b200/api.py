@@ -180,10 +180,17 @@ def TensorACA_rect(bs: int, src: torch.Tensor, tar: torch.Tensor, scale, div) ->
         L = lib()
         tar, src = tar.contiguous(), src.contiguous()
         H = torch.empty((bs, 3, 3), dtype=tar.dtype, device=tar.device)
+        on_dev = all(torch.is_tensor(x) and x.device == tar.device and x.dtype == tar.dtype and x.numel() == 1
+                     for x in (scale, div))
         with torch.cuda.device(tar.device):
-            fn = getattr(L.c, f"sks_cuda_aca_rect_planar_{_SUFFIX[tar.dtype]}")
-            L.check(fn(_ptr(tar), _ptr(src), 0.0, 0.0, float(scale), float(div), _ptr(H), bs, 0, None,
-                       _stream_ptr(tar)), "sks_cuda_aca_rect_planar")
+            if on_dev:      # the reference's own calling convention: scale / div are device tensors; no sync
+                fn = getattr(L.c, f"sks_cuda_aca_rect_planar_dev_{_SUFFIX[tar.dtype]}")
+                L.check(fn(_ptr(tar), _ptr(src), _ptr(scale.contiguous()), _ptr(div.contiguous()), _ptr(H), bs, 0,
+                           None, _stream_ptr(tar)), "sks_cuda_aca_rect_planar_dev")
+            else:
+                fn = getattr(L.c, f"sks_cuda_aca_rect_planar_{_SUFFIX[tar.dtype]}")
+                L.check(fn(_ptr(tar), _ptr(src), 0.0, 0.0, float(scale), float(div), _ptr(H), bs, 0, None,
+                           _stream_ptr(tar)), "sks_cuda_aca_rect_planar")
         return H
     tarq = tar[:, :2, :].transpose(1, 2).reshape(bs, 8)
     M = src[:, :2, 0].contiguous()

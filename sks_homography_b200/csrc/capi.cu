@@ -231,7 +231,8 @@ int launch_gather_solve(const T* pool, uint32_t pool_size, const uint32_t* rand4
 
 template <typename T>
 int launch_rect_planar(const T* tar34, const T* src34, RectParams<T> rp, T* H, int64_t n, int flags,
-                       uint8_t* degen, void* stream)
+                       uint8_t* degen, void* stream, const T* width_dev = nullptr,
+                       const T* ratio_dev = nullptr)
 {
     if (n < 0 || (flags & ~SKS_FLAG_NORMALIZE)) return SKS_ERR_INVALID_ARG;
     if (n > 0 && (tar34 == nullptr || H == nullptr)) return SKS_ERR_INVALID_ARG;
@@ -242,7 +243,7 @@ int launch_rect_planar(const T* tar34, const T* src34, RectParams<T> rp, T* H, i
     constexpr int TILE = sizeof(T) == 4 ? 256 : 128;
     const int64_t grid = (n + TILE - 1) / TILE;
     k_rect_planar34<T, TILE><<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(
-        tar34, src34, rp, H, degen, n, (flags & SKS_FLAG_NORMALIZE) != 0);
+        tar34, src34, rp, H, degen, n, (flags & SKS_FLAG_NORMALIZE) != 0, width_dev, ratio_dev);
     return finish_launch();
 }
 
@@ -349,6 +350,23 @@ int sks_cuda_aca_rect_planar_f64(const double* tar34, const double* src34, doubl
 {
     return launch_rect_planar<double>(tar34, src34, RectParams<double>{mx, my, width, ratio}, H, n,
                                       flags, degenerate, stream);
+}
+
+int sks_cuda_aca_rect_planar_dev_f32(const float* tar34, const float* src34, const float* width_dev,
+                                     const float* ratio_dev, float* H, int64_t n, int flags,
+                                     uint8_t* degenerate, void* stream)
+{
+    if (width_dev == nullptr || ratio_dev == nullptr) return SKS_ERR_INVALID_ARG;
+    return launch_rect_planar<float>(tar34, src34, RectParams<float>{0.f, 0.f, 0.f, 0.f}, H, n, flags, degenerate,
+                                     stream, width_dev, ratio_dev);
+}
+int sks_cuda_aca_rect_planar_dev_f64(const double* tar34, const double* src34, const double* width_dev,
+                                     const double* ratio_dev, double* H, int64_t n, int flags,
+                                     uint8_t* degenerate, void* stream)
+{
+    if (width_dev == nullptr || ratio_dev == nullptr) return SKS_ERR_INVALID_ARG;
+    return launch_rect_planar<double>(tar34, src34, RectParams<double>{0., 0., 0., 0.}, H, n, flags, degenerate,
+                                      stream, width_dev, ratio_dev);
 }
 
 int sks_cuda_gather_samples_f32(const float* pool, uint32_t pool_size, const uint32_t* rand4,

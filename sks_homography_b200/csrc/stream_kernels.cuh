@@ -248,8 +248,13 @@ k_aos_direct(const T* __restrict__ src, const T* __restrict__ tar, const T* __re
 template <typename T, int TILE>
 __global__ void __launch_bounds__(TILE)
 k_rect_planar34(const T* __restrict__ tar34, const T* __restrict__ src34, RectParams<T> rp,
-                T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, bool normalize)
+                T* __restrict__ H, uint8_t* __restrict__ degen, int64_t n, bool normalize,
+                const T* __restrict__ width_dev, const T* __restrict__ ratio_dev)
 {
+    // the reference passes `scale` and `div` as one-element DEVICE tensors (PY.py:33-35, :301-302);
+    // reading them here keeps the call free of a device->host synchronisation
+    if (width_dev != nullptr) rp.width = __ldg(width_dev);
+    if (ratio_dev != nullptr) rp.ratio = __ldg(ratio_dev);
     __shared__ __align__(32) T stage[TILE * 9];
     constexpr int EPC = ChunkTraits<T>::EPC, NC = 4 / EPC;   // 16-byte chunks per row
     const int tid = threadIdx.x;

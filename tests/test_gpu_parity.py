@@ -203,6 +203,16 @@ def test_reference_torch_interfaces(api, golden, cuda):
     H = api.TensorACA_rect(bs, dev(g["src_new"], cuda), dev(g["tar_new"], cuda),
                            g["scale"].item(), g["div"].item())
     assert_same_bits(H.cpu().numpy(), g["H_rect"], "TensorACA_rect")
+    # the reference's own calling convention: scale / div as one-element DEVICE tensors (PY.py:33-35),
+    # read by the kernel -- no host synchronisation
+    for dt in (np.float32, np.float64):
+        Hd = api.TensorACA_rect(bs, dev(g["src_new"].astype(dt), cuda), dev(g["tar_new"].astype(dt), cuda),
+                                dev(g["scale"].astype(dt), cuda), dev(g["div"].astype(dt), cuda))
+        Hs = api.TensorACA_rect(bs, dev(g["src_new"].astype(dt), cuda), dev(g["tar_new"].astype(dt), cuda),
+                                float(g["scale"].astype(dt).item()), float(g["div"].astype(dt).item()))
+        assert_same_bits(Hd.cpu().numpy(), Hs.cpu().numpy(), f"TensorACA_rect device scalars {dt.__name__}")
+        if dt == np.float32:
+            assert_same_bits(Hd.cpu().numpy(), g["H_rect"], "TensorACA_rect device scalars")
     Hv = api.ACA_vanilla(bs, dev(g["src"], cuda), dev(g["tar"], cuda))
     assert_same_bits(Hv.cpu().numpy(), g["H_vanilla"], "ACA_vanilla")
 

@@ -21,6 +21,7 @@ case "$stage" in
   pcie_multi)   N=${NGPU:-2}; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29556 tools/pcie_multi_probe.py 2> gpurun_out/pcie_multi_n$N.err | tee gpurun_out/pcie_multi_probe_n$N.log; tail -3 gpurun_out/pcie_multi_n$N.err ;;
   wring_sweep)  timeout 900 python tools/wring_sweep.py 2>&1 | tee gpurun_out/wring_sweep.log ;;
   parity_tests) timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 2>&1 | tail -5 | tee gpurun_out/parity_tests.log ;;
+  ncu_headline) timeout 300 python tools/headline_once.py > gpurun_out/headline_plain.log 2>&1 && timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_aos_direct -s 2 -c 1 -f -o gpurun_out/headline python tools/headline_once.py > gpurun_out/ncu_headline.log 2>&1; tail -2 gpurun_out/ncu_headline.log ;;
   *) echo "unknown stage $stage" ;;
 esac
 done
