@@ -878,8 +878,8 @@ def measure_ransac(cx, steps, warmup, shard="hypotheses", peer_reduce=False, bre
 
 def measure_ransac_inprocess(cx, steps=5):
     """The single-process multi-GPU driver behind the C ABI (sks_cuda_ransac_aca_multi_f32, csrc/multi.cu):
-    rank 0 alone drives `world` GPUs -- matches on its own device, the others read them over NVLink peer
-    access and merge their winners with peer atomics -- while the other ranks wait at a barrier."""
+    rank 0 alone drives `world` GPUs -- matches on its own device, broadcast to the others over NVLink,
+    winners merged with peer atomics -- while the other ranks block on the host with their GPUs idle."""
     torch, api, args = cx.torch, cx.api, cx.args
 
     def work():
@@ -901,8 +901,9 @@ def measure_ransac_inprocess(cx, steps=5):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            return {"api": "sks_cuda_ransac_aca_multi_f32 (one process, one enqueueing thread, NVLink peer reads + "
-                           "peer atomics, CUDA-event ordering; no NCCL, no IPC)", "gpus": ngpu, "steps": steps,
+            return {"api": "sks_cuda_ransac_aca_multi_f32 (one process, one enqueueing thread, matches broadcast by a "
+                           "binomial tree of NVLink peer copies, winners merged by peer atomics, CUDA-event ordering; "
+                           "no NCCL, no IPC)", "gpus": ngpu, "steps": steps,
                     "ms_per_step": ms, "value": P * n_hyp / (ms * 1e-3), "unit": "hypotheses/s",
                     "other_ranks": "blocked on the host (rendezvous store), GPUs idle",
                     "bit_identical_to_one_gpu": bool(torch.equal(kn, k1) and torch.equal(cn, c1) and
