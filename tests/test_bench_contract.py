@@ -30,6 +30,17 @@ def test_reference_arm_line(reflib):
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and "workload" in d["config"]
 
 
+def test_both_arms_describe_the_same_config(reflib):
+    """The driver compares the two arms' `config` dicts: the reference arm must print exactly what our arm
+    prints for the headline workload (BASELINE configs[1]), whatever its bounded sample is."""
+    sys.path.insert(0, ROOT)
+    import bench
+    solver, dt, bph, log2n, dist = bench.WORKLOADS["aca_f32"]
+    ours = bench.stream_config(solver, dt, log2n, "aos", True, False, 1 << log2n, bph, 11, dist)
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "3", "--ref-log2n", "14")
+    assert d["config"] == ours and "2^26" in ours["workload"] and ours["quadruples_per_gpu"] == 1 << 26
+
+
 def test_reference_arm_non_zero_ranks_exit_quietly():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"},
