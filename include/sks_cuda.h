@@ -170,6 +170,10 @@ int sks_host_set_device_count(int count);
 /* Pipeline granularity of the host-pointer path: bytes of ONE input array per chunk
  * (upper bound, default 64 MiB; 64 KiB .. 1 GiB; batches are cut into ~8 chunks). */
 int sks_host_set_chunk_bytes(int64_t bytes_per_input_array);
+/* Staging copies of the pageable path: bit 0 = non-temporal (streaming) stores into the pinned
+ * ring, bit 1 = out of it into the caller's result buffer; 0 = plain memcpy both ways.
+ * A tuning knob for measurements; every setting gives the same bytes. */
+int sks_host_set_staging_copy(int non_temporal);
 /* pinned host allocation helpers for callers that want the zero-staging path */
 int sks_host_alloc_pinned(void **ptr, int64_t bytes);
 int sks_host_free_pinned(void *ptr);

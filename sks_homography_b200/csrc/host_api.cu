@@ -162,6 +162,42 @@ bool is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+// Staging copy with non-temporal stores (SSE2, baseline x86-64).  The pageable path is bound by the
+// host's memory system, not by PCIe: per homography 64 B are copied into the pinned ring and 36 B out
+// of it, and an ordinary store to a line that is not in cache first READS the line (read for
+// ownership), so a plain memcpy moves 3 bytes over the memory bus per byte copied.  Streaming stores
+// skip that read and keep the (never re-read) staging data out of the caches.
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+static void stream_copy(void* dst, const void* src, size_t n)
+{
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    if (head > n) head = n;
+    std::memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+        s += 64; d += 64;
+    }
+    std::memcpy(d, s, n - blocks * 64);
+    _mm_sfence();
+}
+#else
+static void stream_copy(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); }
+#endif
+std::atomic<int> g_stream_copy{3};     // sks_host_set_staging_copy: bit 0 = non-temporal stores into the pinned ring,
+                                       // bit 1 = non-temporal stores out of it into the caller's result buffer
+
 // Persistent memcpy workers for the pageable staging path: spawning threads per copy costs
 // about as much as copying a few MiB, and the in- and out-stagers copy at the same time.
 class CopyPool {
@@ -172,12 +208,12 @@ public:
         return *p;
     }
     // copy [src, src+bytes) to dst in slices of >= 1 MiB on up to `max_parts` workers; blocks
-    void copy(void* dst, const void* src, size_t bytes, unsigned max_parts)
+    void copy(void* dst, const void* src, size_t bytes, unsigned max_parts, bool nt)
     {
         const unsigned parts = (unsigned)std::min<size_t>(std::min<size_t>(max_parts, workers_.size()),
                                                           bytes / (1u << 20) + 1);
         if (parts <= 1 || workers_.empty()) {
-            std::memcpy(dst, src, bytes);
+            if (nt) stream_copy(dst, src, bytes); else std::memcpy(dst, src, bytes);
             return;
         }
         Job job;
@@ -187,7 +223,7 @@ public:
             std::lock_guard<std::mutex> g(m_);
             for (unsigned t = 0; t < parts; ++t) {
                 const size_t lo = std::min(bytes, per * t), hi = (t + 1 == parts) ? bytes : std::min(bytes, lo + per);
-                q_.push_back(Task{(char*)dst + lo, (const char*)src + lo, hi - lo, &job});
+                q_.push_back(Task{(char*)dst + lo, (const char*)src + lo, hi - lo, &job, nt});
             }
         }
         cv_.notify_all();
@@ -206,6 +242,7 @@ private:
         const char* src;
         size_t bytes;
         Job* job;
+        bool nt;
     };
     CopyPool()
     {
@@ -224,7 +261,9 @@ private:
                 t = q_.front();
                 q_.pop_front();
             }
-            if (t.bytes) std::memcpy(t.dst, t.src, t.bytes);
+            if (t.bytes) {
+                if (t.nt) stream_copy(t.dst, t.src, t.bytes); else std::memcpy(t.dst, t.src, t.bytes);
+            }
             std::lock_guard<std::mutex> g(t.job->m);
             if (--t.job->left == 0) t.job->cv.notify_one();
         }
@@ -235,10 +274,59 @@ private:
     std::vector<std::thread> workers_;
 };
 
-void parallel_copy(void* dst, const void* src, size_t bytes)
+void parallel_copy(void* dst, const void* src, size_t bytes, bool nt)
 {
-    CopyPool::get().copy(dst, src, bytes, 8);
+    CopyPool::get().copy(dst, src, bytes, 8, nt);
 }
+
+}  // namespace
+
+// H2D copy of a host array that may be pageable, for the RANSAC host entries (also csrc/multi.cu):
+// pinned sources go out as one cudaMemcpyAsync; pageable ones are cut into 8 MiB pieces that a
+// worker pool copies (non-temporal stores) into two alternating pinned buffers while the previous
+// piece is on the bus -- cudaMemcpyAsync straight from pageable memory managed ~13 GB/s here.
+// `sb` holds the two pinned buffers and their events (owned by the caller's per-device context).
+struct SksStageBuf {
+    void* p[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+};
+extern "C" int sks_stage_h2d_internal(void* dst, const void* src, size_t bytes, cudaStream_t st, SksStageBuf* sb)
+{
+    constexpr size_t PIECE = 8u << 20;
+    if (bytes == 0) return SKS_OK;
+    if (is_pinned(src) || bytes < (1u << 20)) {
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+        return e == cudaSuccess ? SKS_OK : (int)e;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (sb->p[i] == nullptr) {
+            CK(cudaHostAlloc(&sb->p[i], PIECE, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&sb->ev[i], cudaEventDisableTiming));
+            sb->used[i] = false;
+        }
+    const bool nt = (g_stream_copy.load() & 1) != 0;
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += PIECE, i ^= 1) {
+        const size_t n = bytes - off < PIECE ? bytes - off : PIECE;
+        if (sb->used[i]) CK(cudaEventSynchronize(sb->ev[i]));      // the DMA that last read this buffer
+        parallel_copy(sb->p[i], static_cast<const char*>(src) + off, n, nt);
+        CK(cudaMemcpyAsync(static_cast<char*>(dst) + off, sb->p[i], n, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(sb->ev[i], st));
+        sb->used[i] = true;
+    }
+    return SKS_OK;
+}
+extern "C" void sks_stage_free_internal(SksStageBuf* sb)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (sb->ev[i]) { cudaEventSynchronize(sb->ev[i]); cudaEventDestroy(sb->ev[i]); }
+        if (sb->p[i]) cudaFreeHost(sb->p[i]);
+        sb->p[i] = nullptr; sb->ev[i] = nullptr; sb->used[i] = false;
+    }
+}
+
+namespace {
 
 // Generic pipeline.  in[k] (k < n_in) are host arrays of in_elems[k] elements
 // per quadruple; out is 9 elements per quadruple; `launch` enqueues the solver
@@ -251,6 +339,11 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
     bool stage_in = false;
     for (int k = 0; k < n_in; ++k) stage_in = stage_in || !is_pinned(in[k]);
     const bool stage_out = !is_pinned(out);
+    // non-temporal staging copies (measured on B200 hosts, tools/host_pageable_probe.py): into the ring
+    // always (0.40 -> 0.55 G H/s with pageable in/out); out of it when the input is staged as well and
+    // the host's memory bus is the bottleneck (0.55 -> 0.59), not when only the output is (0.72 -> 0.68)
+    const bool nt_in = (g_stream_copy.load() & 1) != 0;
+    const bool nt_out = (g_stream_copy.load() & 2) != 0 && stage_in;
     // staged (pageable) batches use smaller chunks: the two host memcpys overlap the DMA at a
     // finer grain and the pipeline fills sooner
     const int64_t cap_bytes = (stage_in || stage_out) ? std::min<int64_t>(g_chunk_bytes.load(), 16ll << 20)
@@ -320,7 +413,7 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
                 if (stage_in)
                     for (int k = 0; k < n_in; ++k)
                         parallel_copy(sl.p_in[k], in[k] + off * in_elems[k],
-                                      (size_t)cnt * in_elems[k] * sizeof(T));
+                                      (size_t)cnt * in_elems[k] * sizeof(T), nt_in);
                 std::lock_guard<std::mutex> g(m);
                 staged = ci + 1;
                 cv.notify_all();
@@ -339,7 +432,7 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
                 if (e != cudaSuccess) { fail((int)e); break; }
                 const int64_t off = offs[ci], cnt = cnts[ci];
                 if (stage_out)
-                    parallel_copy(out + off * 9, sl.p_out, (size_t)cnt * 9 * sizeof(T));
+                    parallel_copy(out + off * 9, sl.p_out, (size_t)cnt * 9 * sizeof(T), nt_out);
                 std::lock_guard<std::mutex> g(m);
                 freed = ci + 1;
                 cv.notify_all();
@@ -380,7 +473,7 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
         if (s.pending_off < 0) return SKS_OK;
         CK(cudaEventSynchronize(s.done));
         if (stage_out)
-            parallel_copy(out + s.pending_off * 9, s.p_out, (size_t)s.pending_cnt * 9 * sizeof(T));
+            parallel_copy(out + s.pending_off * 9, s.p_out, (size_t)s.pending_cnt * 9 * sizeof(T), nt_out);
         s.pending_off = -1;
         return SKS_OK;
     };
@@ -396,7 +489,7 @@ int run_on_device(int dev, const T* const* in, const int* in_elems, int n_in, T*
             const size_t bytes = (size_t)cnt * in_elems[k] * sizeof(T);
             const T* hsrc = in[k] + off * in_elems[k];
             if (stage_in) {
-                parallel_copy(s.p_in[k], hsrc, bytes);
+                parallel_copy(s.p_in[k], hsrc, bytes, nt_in);
                 hsrc = static_cast<const T*>(s.p_in[k]);
             }
             cu(cudaMemcpyAsync(s.d_in[k], hsrc, bytes, cudaMemcpyHostToDevice, s.stream));
@@ -545,6 +638,7 @@ struct RansacHostCtx {
     cudaStream_t stream = nullptr;
     void* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // corr, H, cnt, key, samples, mask
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    SksStageBuf stage;
 };
 static std::vector<RansacHostCtx*> g_ransac_ctx;      // guarded by g_mu
 
@@ -599,8 +693,8 @@ int sks_host_ransac_aca_f32(const float* corr, int64_t n_pairs, int32_t n_pts, c
     uint8_t* d_mask = inlier_mask ? static_cast<uint8_t*>(c->buf[5]) : nullptr;
     int rc = SKS_OK;
     auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == SKS_OK) rc = (int)e; return rc == SKS_OK; };
-    cu(cudaMemcpyAsync(d_corr, corr, need[0], cudaMemcpyHostToDevice, st));
-    if (rc == SKS_OK && samples) cu(cudaMemcpyAsync(d_samp, samples, need[4], cudaMemcpyHostToDevice, st));
+    rc = sks_stage_h2d_internal(d_corr, corr, need[0], st, &c->stage);
+    if (rc == SKS_OK && samples) rc = sks_stage_h2d_internal(d_samp, samples, need[4], st, &c->stage);
     if (rc == SKS_OK) cu(cudaMemsetAsync(d_key, 0, need[3], st));
     if (rc == SKS_OK)
         rc = sks_cuda_ransac_aca_f32(d_corr, n_pairs, n_pts, d_samp, n_hyp, 0, n_hyp, seed, thr2, d_key, st);
@@ -641,6 +735,13 @@ int sks_host_set_chunk_bytes(int64_t bytes_per_input_array)
     return SKS_OK;
 }
 
+int sks_host_set_staging_copy(int non_temporal)
+{
+    if (non_temporal < 0 || non_temporal > 3) return SKS_ERR_INVALID_ARG;
+    g_stream_copy.store(non_temporal);
+    return SKS_OK;
+}
+
 int sks_host_set_device_count(int count)
 {
     if (count < 0) return SKS_ERR_INVALID_ARG;
@@ -661,6 +762,7 @@ int sks_cuda_shutdown(void)
     for (RansacHostCtx* c : g_ransac_ctx) {
         { std::lock_guard<std::mutex> busy(c->mu); }
         cudaSetDevice(c->device);
+        sks_stage_free_internal(&c->stage);
         for (void* b : c->buf)
             if (b) cudaFree(b);
         if (c->stream) cudaStreamDestroy(c->stream);

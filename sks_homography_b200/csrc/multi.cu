@@ -26,6 +26,15 @@
 
 #include "../../include/sks_cuda.h"
 
+// pageable-aware H2D copy shared with csrc/host_api.cu
+struct SksStageBuf {
+    void* p[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+};
+extern "C" int sks_stage_h2d_internal(void* dst, const void* src, size_t bytes, cudaStream_t st, SksStageBuf* sb);
+extern "C" void sks_stage_free_internal(SksStageBuf* sb);
+
 namespace {
 
 #define CK(x)                                  \
@@ -69,6 +78,7 @@ struct MultiCtx {
     size_t corr_cap = 0;
     uint32_t* samples = nullptr;
     size_t samples_cap = 0;
+    SksStageBuf stage;
 };
 
 std::mutex g_mu;
@@ -291,8 +301,8 @@ int sks_host_ransac_aca_multi_f32(const float* corr, int64_t n_pairs, int32_t n_
 
     int rc = SKS_OK;
     auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == SKS_OK) rc = (int)e; return e == cudaSuccess; };
-    cu(cudaMemcpyAsync(c->corr, corr, corr_bytes, cudaMemcpyHostToDevice, st));
-    if (rc == SKS_OK && samples) cu(cudaMemcpyAsync(c->samples, samples, samp_bytes, cudaMemcpyHostToDevice, st));
+    rc = sks_stage_h2d_internal(c->corr, corr, corr_bytes, st, &c->stage);
+    if (rc == SKS_OK && samples) rc = sks_stage_h2d_internal(c->samples, samples, samp_bytes, st, &c->stage);
     if (rc == SKS_OK)
         rc = enqueue_sharded(c, ngpu, c->corr, samples ? c->samples : nullptr, n_pairs, n_pts, n_hyp, seed, thr2,
                              d_key, st);
@@ -331,6 +341,7 @@ void sks_multi_shutdown_internal(void)
             if (p.corr) cudaFree(p.corr);
         }
         cudaSetDevice(c->primary);
+        sks_stage_free_internal(&c->stage);
         if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
         if (c->ready) cudaEventDestroy(c->ready);
         for (void* b : c->buf)
