@@ -50,6 +50,9 @@
 #ifndef SKS_RANSAC_MIN_CTAS
 #define SKS_RANSAC_MIN_CTAS(T) ((T) <= 256 ? 3 : (T) <= 384 ? 2 : 1)
 #endif
+#ifndef SKS_RANSAC_FP_JOINT
+#define SKS_RANSAC_FP_JOINT 0
+#endif
 #ifndef SKS_RANSAC_HYP_MAJOR
 #define SKS_RANSAC_HYP_MAJOR 1
 #endif
@@ -211,52 +214,82 @@ constexpr float kRansacFpCount0 = 16777215.0f;
 // packed FMA that needs a third register from one bank occupies the pipe for three cycles
 // instead of two (tools/ubench/count_ops.cu: 3.03 vs 2.04 cycles).  Same operations per
 // hypothesis x match as ransac_inlier2_fp, so the same bits.
+template <int HPT, int NP>
+__device__ __forceinline__ void ransac_score_pairs_fp(const float (&g)[HPT][9], const float4 (&c)[2 * NP],
+                                                      float2 (&fc)[HPT])
+{
+    // NP match pairs x HPT hypotheses per phase: each phase is NP*HPT (x3 in the first two)
+    // independent instructions, long enough to cover the packed FMA's latency, so a warp keeps
+    // issuing across phase boundaries (and keeps its operand-reuse cache) instead of yielding
+    float2 u[NP][HPT], v[NP][HPT], w[NP][HPT];
+#define SKS_B(j, k) make_float2(g[j][k], g[j][k])
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {                        // phase 1: y in slot b
+        const float2 y = make_float2(c[2 * p].z, c[2 * p].w);
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) {
+            u[p][j] = __ffma2_rn(SKS_B(j, 1), y, SKS_B(j, 2));
+            v[p][j] = __ffma2_rn(SKS_B(j, 4), y, SKS_B(j, 5));
+            w[p][j] = __ffma2_rn(SKS_B(j, 7), y, SKS_B(j, 8));
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {                        // phase 2: x in slot b
+        const float2 x = make_float2(c[2 * p].x, c[2 * p].y);
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) {
+            u[p][j] = __ffma2_rn(SKS_B(j, 0), x, u[p][j]);
+            v[p][j] = __ffma2_rn(SKS_B(j, 3), x, v[p][j]);
+            w[p][j] = __ffma2_rn(SKS_B(j, 6), x, w[p][j]);
+        }
+    }
+#undef SKS_B
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {                        // phase 3: residuals; w[j] shared in slot b,
+        const float2 nX = make_float2(c[2 * p + 1].x, c[2 * p + 1].y);   // -Xs / -Ys shared in slot a
+        const float2 nY = make_float2(c[2 * p + 1].z, c[2 * p + 1].w);
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) {
+            if (j & 1) {
+                v[p][j] = __ffma2_rn(nY, w[p][j], v[p][j]);
+                u[p][j] = __ffma2_rn(nX, w[p][j], u[p][j]);
+            } else {
+                u[p][j] = __ffma2_rn(nX, w[p][j], u[p][j]);
+                v[p][j] = __ffma2_rn(nY, w[p][j], v[p][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int j = 0; j < HPT; ++j)
+            u[p][j] = __fmul2_rn(u[p][j], u[p][j]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int j = 0; j < HPT; ++j)
+            u[p][j] = __ffma2_rn(v[p][j], v[p][j], u[p][j]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) {
+            const float2 nw = make_float2(-w[p][j].x, -w[p][j].y);   // exact; ptxas folds it into FFMA2's operand negation
+            u[p][j] = __ffma2_rn(nw, w[p][j], u[p][j]);
+        }
+    const float tiny = __uint_as_float(1u);
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int j = 0; j < HPT; ++j)
+            fc[j] = __ffma2_rd(u[p][j], make_float2(tiny, tiny), fc[j]);
+}
+
 template <int HPT>
 __device__ __forceinline__ void ransac_score_pair_fp(const float (&g)[HPT][9], const float4 p0,
                                                      const float4 p1, float2 (&fc)[HPT])
 {
-    const float2 x = make_float2(p0.x, p0.y), y = make_float2(p0.z, p0.w);
-    const float2 nX = make_float2(p1.x, p1.y), nY = make_float2(p1.z, p1.w);
-    float2 u[HPT], v[HPT], w[HPT];
-#define SKS_B(j, k) make_float2(g[j][k], g[j][k])
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) {                       // phase 1: y in slot b
-        u[j] = __ffma2_rn(SKS_B(j, 1), y, SKS_B(j, 2));
-        v[j] = __ffma2_rn(SKS_B(j, 4), y, SKS_B(j, 5));
-        w[j] = __ffma2_rn(SKS_B(j, 7), y, SKS_B(j, 8));
-    }
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) {                       // phase 2: x in slot b
-        u[j] = __ffma2_rn(SKS_B(j, 0), x, u[j]);
-        v[j] = __ffma2_rn(SKS_B(j, 3), x, v[j]);
-        w[j] = __ffma2_rn(SKS_B(j, 6), x, w[j]);
-    }
-#undef SKS_B
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) {                       // phase 3: residuals, w[j] shared in slot b,
-        if (j & 1) {                                      // -Xs / -Ys shared in slot a across hypotheses
-            v[j] = __ffma2_rn(nY, w[j], v[j]);
-            u[j] = __ffma2_rn(nX, w[j], u[j]);
-        } else {
-            u[j] = __ffma2_rn(nX, w[j], u[j]);
-            v[j] = __ffma2_rn(nY, w[j], v[j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)
-        u[j] = __fmul2_rn(u[j], u[j]);
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)
-        u[j] = __ffma2_rn(v[j], v[j], u[j]);
-    const float tiny = __uint_as_float(1u);
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) {
-        const float2 nw = make_float2(-w[j].x, -w[j].y);   // exact; ptxas folds it into FFMA2's operand negation
-        u[j] = __ffma2_rn(nw, w[j], u[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)
-        fc[j] = __ffma2_rd(u[j], make_float2(tiny, tiny), fc[j]);
+    const float4 c[2] = {p0, p1};
+    ransac_score_pairs_fp<HPT, 1>(g, c, fc);
 }
 
 // Second packed form: TWO HYPOTHESES per instruction, one match.  g[k] = (gA_k, gB_k)
@@ -411,9 +444,14 @@ __device__ __forceinline__ bool ransac_pass(RansacTileStream& ts, int64_t pair, 
 #pragma unroll
                     for (int k = 0; k < 2 * SKS_RANSAC_FP_UNROLL; ++k)
                         c[k] = tile[2 * i + k];   // warp-uniform address: broadcast
+#if SKS_RANSAC_FP_JOINT     // all pairs of the iteration phase by phase: measured 100.9 vs 96.3 ms (ptxas
+                            // re-serialises the pairs under the 80-register cap and schedules them worse)
+                    ransac_score_pairs_fp<kRansacHpt, SKS_RANSAC_FP_UNROLL>(h, c, fc);
+#else
 #pragma unroll
                     for (int k = 0; k < SKS_RANSAC_FP_UNROLL; ++k)
                         ransac_score_pair_fp<kRansacHpt>(h, c[2 * k], c[2 * k + 1], fc);
+#endif
                 }
                 for (; i < npair; ++i)
                     ransac_score_pair_fp<kRansacHpt>(h, tile[2 * i], tile[2 * i + 1], fc);
