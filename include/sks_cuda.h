@@ -361,7 +361,9 @@ int sks_cuda_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t
  * reset (bench.py reports it as gpu_launches). */
 int64_t sks_cuda_launch_count(void);
 void sks_cuda_reset_launch_count(void);
-/* Kernel variant for the AoS streaming solvers: 0 = default (best measured, = 1),
+/* The three tuning setters below act on the CALLING HOST THREAD only (thread-local state): a
+ * setting never changes what another thread's calls launch.
+ * Kernel variant for the AoS streaming solvers: 0 = default (best measured, = 1),
  * 1 = direct vector loads + shared-memory transposed stores,
  * 2 = persistent TMA bulk-copy ring (cp.async.bulk + mbarrier); 2 also keeps the fused
  * gather+solve entry points on their L1 gather path instead of the shared-memory-pool kernel;

@@ -23,16 +23,23 @@ using namespace sksb;
 namespace {
 
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_variant{0};        // 0 default, 1 direct, 2 ring, 3 warp-private ring
-std::atomic<int> g_tile_small{0};     // ring tile: 0 = 256/128 (f32/f64), 1 = 128/64
-std::atomic<int> g_stages{4};
-std::atomic<int> g_ctas_per_sm{0};    // 0 = whatever the occupancy calculator allows
-std::atomic<int> g_wide{1};           // direct kernel: 256-bit loads/stores when 32-byte aligned
-std::atomic<int> g_ransac_hpt{2};     // hypotheses per thread in the RANSAC kernel (2 or 4)
-std::atomic<int> g_ransac_packed{3};  // scorer: 0 scalar FFMA, 1 FFMA2 over two matches, 2 FFMA2 over two hypotheses,
-                                      // 3 (default) = 1 with the inlier count on the FP32 pipe (FFMA2.RM)
-std::atomic<int> g_ransac_threads{256};
-std::atomic<int> g_ransac_rounds{8};  // rounds per CTA (chunk = rounds * 256 * hpt hypotheses)
+// Kernel tuning knobs (sks_cuda_set_variant / _tuning / _ransac_tuning).  They are PER HOST THREAD:
+// a setting made by one thread never changes what another thread's calls launch (round-1 review: the
+// knobs used to be process-global).  Worker threads the library starts itself (host_api.cu) inherit
+// the caller's settings through sks_tuning_get_internal / sks_tuning_set_internal.
+struct Tuning {
+    int variant = 0;          // 0 default, 1 direct, 2 ring, 3 warp-private ring
+    int tile_small = 0;       // ring tile: 0 = 256/128 (f32/f64), 1 = 128/64
+    int stages = 4;
+    int ctas_per_sm = 0;      // 0 = whatever the occupancy calculator allows
+    int wide = 1;             // direct kernel: 256-bit loads/stores when 32-byte aligned
+    int ransac_hpt = 2;       // hypotheses per thread in the RANSAC kernel (2 or 4)
+    int ransac_packed = 3;    // scorer: 0 scalar FFMA, 1 FFMA2 over two matches, 2 FFMA2 over two hypotheses,
+                              // 3 (default) = 1 with the inlier count on the FP32 pipe (FFMA2.RM)
+    int ransac_threads = 256;
+    int ransac_rounds = 8;    // rounds per CTA (chunk = rounds * 256 * hpt hypotheses)
+};
+thread_local Tuning t_tuning;
 
 struct DevInfo {
     int sms = 0;
@@ -79,7 +86,7 @@ int launch_ring(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, 
 {
     using L = RingLayout<SOLVER, T, TILE>;
     auto kern = k_aos_ring<SOLVER, T, TILE>;
-    int stages = g_stages.load();
+    int stages = t_tuning.stages;
     if (stages < 2) stages = 2;
     while (stages > 2 && L::smem_bytes(stages) > dev.smem_optin) --stages;
     const int smem = L::smem_bytes(stages);
@@ -89,7 +96,7 @@ int launch_ring(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H, 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
-    const int want = g_ctas_per_sm.load();
+    const int want = t_tuning.ctas_per_sm;
     if (want > 0 && want < occ) occ = want;
     const int64_t n_tiles = (n + TILE - 1) / TILE;
     const int64_t grid = n_tiles < (int64_t)dev.sms * occ ? n_tiles : (int64_t)dev.sms * occ;
@@ -120,7 +127,7 @@ int launch_wring(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H,
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
-    const int want = g_ctas_per_sm.load();
+    const int want = t_tuning.ctas_per_sm;
     if (want > 0 && want < occ) occ = want;
     const int64_t n_tiles = (n + QPW - 1) / QPW;
     const int64_t ctas_needed = (n_tiles + WARPS - 1) / WARPS;
@@ -165,7 +172,7 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
         return finish_launch();
     }
 
-    int variant = g_variant.load();
+    int variant = t_tuning.variant;
     if (variant == 0) variant = 1;   // measured best on B200 (profiles/): direct > ring
 #ifndef SKS_DIRECT_TILE_F32
 #define SKS_DIRECT_TILE_F32 256
@@ -174,7 +181,7 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
     constexpr int SMALL = BIG / 2;
     if (variant == 1) {
         const int64_t grid = (n + BIG - 1) / BIG;
-        const bool wide = g_wide.load() && aligned32(H) && aligned32(tar) && (!src || aligned32(src));
+        const bool wide = t_tuning.wide && aligned32(H) && aligned32(tar) && (!src || aligned32(src));
         if (wide)
             k_aos_direct<SOLVER, T, BIG, true><<<(unsigned)grid, BIG, 0, st>>>(src, tar, M, rp, H,
                                                                                degen, n, normalize);
@@ -189,7 +196,7 @@ int launch_stream(const T* src, const T* tar, const T* M, RectParams<T> rp, T* H
         else
             return launch_wring<SOLVER, T>(src, tar, M, rp, H, degen, n, normalize, dev, st);
     }
-    if (g_tile_small.load())
+    if (t_tuning.tile_small)
         return launch_ring<SOLVER, T, SMALL>(src, tar, M, rp, H, degen, n, normalize, dev, st);
     return launch_ring<SOLVER, T, BIG>(src, tar, M, rp, H, degen, n, normalize, dev, st);
 }
@@ -213,7 +220,7 @@ int launch_gather_solve(const T* pool, uint32_t pool_size, const uint32_t* rand4
     // from shared memory (variant 2 of sks_cuda_set_variant forces the L1 path for comparison)
     const size_t pool_bytes = (size_t)pool_size * 4 * sizeof(T);
     if (layout == SKS_LAYOUT_SOA && pool_bytes <= 96u * 1024 && n >= (int64_t)dev.sms * 2048 &&
-        g_variant.load() != 2) {
+        t_tuning.variant != 2) {
         auto pk = k_gather_solve_pool<SOLVER, T>;
         cudaError_t e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes);
         if (e != cudaSuccess) return (int)e;
@@ -221,7 +228,7 @@ int launch_gather_solve(const T* pool, uint32_t pool_size, const uint32_t* rand4
             pool, pool_size, rand4, seed_key(seed), H, degen, n, ld, (flags & SKS_FLAG_NORMALIZE) != 0);
         return finish_launch();
     }
-    const bool wide = sizeof(T) == 8 && aligned32(pool) && g_wide.load() != 0;
+    const bool wide = sizeof(T) == 8 && aligned32(pool) && t_tuning.wide != 0;
     auto kern = wide ? k_gather_solve<SOLVER, T, TILE, true> : k_gather_solve<SOLVER, T, TILE, false>;
     kern<<<(unsigned)grid, TILE, 0, static_cast<cudaStream_t>(stream)>>>(
         pool, pool_size, rand4, seed_key(seed), H, degen, n, layout, ld,
@@ -481,9 +488,9 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
     if (n_pairs == 0 || hyp_count == 0) return SKS_OK;
     const int32_t tile_pts = n_pts < kRansacMaxTilePts ? n_pts : kRansacMaxTilePts;
     const int smem = ((tile_pts + 1) & ~1) * 16;
-    const int hpt = g_ransac_hpt.load();
-    const int mode = g_ransac_packed.load();
-    const int threads = g_ransac_threads.load();
+    const int hpt = t_tuning.ransac_hpt;
+    const int mode = t_tuning.ransac_packed;
+    const int threads = t_tuning.ransac_threads;
     using Kern = void (*)(const float4*, int64_t, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
                           uint32_t, uint32_t, uint64_t, float, unsigned long long*, int64_t);
 #define SKS_RANSAC_PICK(T)                                                                        \
@@ -508,9 +515,9 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
     const double slots = (double)dev.sms * occ;
-    uint32_t chunk = round * (uint32_t)g_ransac_rounds.load();
+    uint32_t chunk = round * (uint32_t)t_tuning.ransac_rounds;
     double best_cost = 0;
-    for (uint32_t r = (uint32_t)g_ransac_rounds.load(), first = 1; r >= 1; r /= 2, first = 0) {
+    for (uint32_t r = (uint32_t)t_tuning.ransac_rounds, first = 1; r >= 1; r /= 2, first = 0) {
         const double ctas = (double)((hyp_count + r * round - 1) / (r * round)) * (double)n_pairs;
         const double waves = (double)(int64_t)((ctas + slots - 1) / slots);
         const double cost = (waves < 1 ? 1 : waves) * ((double)r + 0.03);
@@ -705,33 +712,46 @@ int sks_cuda_shard_range(int64_t n, int rank, int world, int64_t* begin, int64_t
 int64_t sks_cuda_launch_count(void) { return g_launches.load(); }
 void sks_cuda_reset_launch_count(void) { g_launches.store(0); }
 
+// for library-owned worker threads (host_api.cu): copy the calling thread's knobs
+void sks_tuning_get_internal(int* out9)
+{
+    const Tuning& t = t_tuning;
+    const int v[9] = {t.variant, t.tile_small, t.stages, t.ctas_per_sm, t.wide, t.ransac_hpt, t.ransac_packed,
+                      t.ransac_threads, t.ransac_rounds};
+    for (int i = 0; i < 9; ++i) out9[i] = v[i];
+}
+void sks_tuning_set_internal(const int* in9)
+{
+    t_tuning = Tuning{in9[0], in9[1], in9[2], in9[3], in9[4], in9[5], in9[6], in9[7], in9[8]};
+}
+
 int sks_cuda_set_variant(int variant)
 {
     if (variant < 0 || variant > 3) return SKS_ERR_INVALID_ARG;
-    g_variant.store(variant);
+    t_tuning.variant = variant;
     return SKS_OK;
 }
-int sks_cuda_get_variant(void) { return g_variant.load(); }
+int sks_cuda_get_variant(void) { return t_tuning.variant; }
 
 int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int packed)
 {
     if ((hyps_per_thread != 2 && hyps_per_thread != 4) || rounds_per_cta < 1 || rounds_per_cta > 1024)
         return SKS_ERR_INVALID_ARG;
-    g_ransac_hpt.store(hyps_per_thread);
-    g_ransac_rounds.store(rounds_per_cta);
-    g_ransac_packed.store(packed & 3);
+    t_tuning.ransac_hpt = hyps_per_thread;
+    t_tuning.ransac_rounds = rounds_per_cta;
+    t_tuning.ransac_packed = packed & 3;
     const int t = packed >> 2;                       // bits 2.. select the CTA size
-    g_ransac_threads.store(t == 1 ? 384 : t == 2 ? 512 : 256);
+    t_tuning.ransac_threads = t == 1 ? 384 : t == 2 ? 512 : 256;
     return SKS_OK;
 }
 
 int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm)
 {
     if (stages < 2 || stages > 16 || ctas_per_sm < 0) return SKS_ERR_INVALID_ARG;
-    g_wide.store((small_tile & 2) ? 0 : 1);          // bit 1: force 16-byte accesses in the direct kernel
-    g_tile_small.store(small_tile & 1);
-    g_stages.store(stages);
-    g_ctas_per_sm.store(ctas_per_sm);
+    t_tuning.wide = (small_tile & 2) ? 0 : 1;          // bit 1: force 16-byte accesses in the direct kernel
+    t_tuning.tile_small = small_tile & 1;
+    t_tuning.stages = stages;
+    t_tuning.ctas_per_sm = ctas_per_sm;
     return SKS_OK;
 }
 

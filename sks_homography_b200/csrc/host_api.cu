@@ -22,6 +22,8 @@
 #include "../../include/sks_cuda.h"
 
 extern "C" void sks_multi_shutdown_internal(void);   // csrc/multi.cu
+extern "C" void sks_tuning_get_internal(int* out9);     // csrc/capi.cu: per-thread tuning knobs
+extern "C" void sks_tuning_set_internal(const int* in9);
 
 namespace {
 
@@ -549,10 +551,13 @@ int run_pipeline(const T* const* in, const int* in_elems, int n_in, T* out, int6
 
     std::vector<int> rcs(g, SKS_OK);
     std::vector<std::thread> workers;
+    int knobs[9];
+    sks_tuning_get_internal(knobs);          // the workers launch with the caller's tuning
     for (int d = 0; d < g; ++d) {
         int64_t begin = 0, count = 0;
         sks_cuda_shard_range(n, d, g, &begin, &count);
         workers.emplace_back([=, &rcs] {
+            sks_tuning_set_internal(knobs);
             const T* sub[3] = {nullptr, nullptr, nullptr};
             for (int k = 0; k < n_in; ++k) sub[k] = in[k] + begin * in_elems[k];
             rcs[d] = run_on_device<T>(d, sub, in_elems, n_in, out + begin * 9, count, launch);

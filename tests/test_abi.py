@@ -104,3 +104,21 @@ def test_only_tests_bench_and_smoke_touch_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M):
                     offenders.append(os.path.join(rel, f))
     assert not offenders, offenders
+
+
+def test_tuning_knobs_are_per_thread(sks):
+    """sks_cuda_set_variant / _tuning act on the calling host thread only (no process-global state)."""
+    import threading
+    seen = {}
+    assert sks.c.sks_cuda_set_variant(2) == 0
+    try:
+        def other():
+            seen["fresh"] = sks.c.sks_cuda_get_variant()
+            sks.c.sks_cuda_set_variant(3)
+            seen["own"] = sks.c.sks_cuda_get_variant()
+        t = threading.Thread(target=other)
+        t.start(); t.join()
+        assert seen == {"fresh": 0, "own": 3}
+        assert sks.c.sks_cuda_get_variant() == 2
+    finally:
+        sks.c.sks_cuda_set_variant(0)

@@ -515,3 +515,35 @@ def test_extreme_magnitudes_overflow_and_denormals(api, oracle, cuda, solver, dt
     tt = (t * dtype(1e-30 if dtype == np.float32 else 1e-250)).astype(dtype)
     assert_same_bits(api.solve(solver, dev(s, cuda), dev(tt, cuda)).cpu().numpy(), oracle.solve(solver, s, tt),
                      "tiny target plane")
+
+
+def test_concurrent_host_calls_from_two_threads(api, oracle, cuda):
+    """Two host threads call the host-pointer entry points at the same time (streaming solver and
+    fused RANSAC): the per-device contexts serialise them, results stay bit-exact."""
+    import threading
+    s, t = oracle.synth_quads(0, (1 << 20) + 5, 3, 1, np.float32)
+    want = oracle.solve("aca", s, t)
+    corr = api.synth_corr(6, 700, seed=2, device=cuda).cpu()
+    wantk = oracle.ransac(corr.numpy(), 512, 5, 2.25)
+    out, errs = {}, []
+
+    def solver():
+        try:
+            for _ in range(3):
+                out["H"] = api.runKernel_ACA(torch.from_numpy(s), torch.from_numpy(t))
+        except Exception as e:
+            errs.append(e)
+
+    def ransac():
+        try:
+            for _ in range(3):
+                out["k"] = api.ransac_host(corr, 512, 5, 2.25)[3]
+        except Exception as e:
+            errs.append(e)
+
+    th = [threading.Thread(target=solver), threading.Thread(target=ransac)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    assert_same_bits(out["H"].numpy(), want, "concurrent host solve")
+    assert np.array_equal(out["k"].numpy().view(np.uint64), wantk)
