@@ -992,6 +992,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the `configs` legs (other BASELINE configs)")
     ap.add_argument("--legs", default="ransac,rect_2p28_strong,sks_f64_2p25,ransac_inprocess_multi")
+    ap.add_argument("--force-legs", action="store_true", help="run the legs although the top level is not the headline "
+                                                              "workload (tests: small sizes)")
+    ap.add_argument("--leg-log2n", type=int, default=None, help="shrink the rect / SKS-f64 legs (tests only)")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="multi-rank runs: do not pin the rank to its GPU's NUMA node")
     args = ap.parse_args()
@@ -1052,7 +1055,7 @@ def main():
 
     # ---- the other BASELINE configs, as short legs in the same process group --------------------
     legs = None
-    if headline and not args.no_legs:
+    if (headline or args.force_legs) and not args.no_legs:
         want = [x for x in args.legs.split(",") if x]
         legs = {}
         if "ransac" in want:
@@ -1060,7 +1063,7 @@ def main():
                                             do_e2e=False, do_cpu=not args.no_cpu)
             log(f"ransac leg: {legs['ransac']['ms_per_step']:.2f} ms/step, frac {legs['ransac']['roofline']['frac']:.3f}")
         if "rect_2p28_strong" in want:
-            r = measure_stream(cx, "rect_f32", 28, True, steps=max(5, args.steps), warmup=3)
+            r = measure_stream(cx, "rect_f32", args.leg_log2n or 28, True, steps=max(5, args.steps), warmup=3)
             legs["rect_2p28_strong"] = {
                 "config": "BASELINE configs[2]: ACA-rect fp32, 2^28 quadruples in TOTAL, shared source rectangle, "
                           f"contiguous shards over {world} GPU(s), no collective",
@@ -1069,7 +1072,7 @@ def main():
             torch.cuda.empty_cache()
             log(f"rect 2^28 strong: {r['value'] / 1e9:.1f} G H/s")
         if "sks_f64_2p25" in want:
-            r = measure_stream(cx, "sks_f64", 25, False, steps=max(5, args.steps), warmup=3, keep=True)
+            r = measure_stream(cx, "sks_f64", args.leg_log2n or 25, False, steps=max(5, args.steps), warmup=3, keep=True)
             s2, t2, H2 = r.pop("tensors")
             legs["sks_f64_2p25"] = {
                 "config": f"BASELINE configs[3]: SKS fp64, 2^25 quadruples per GPU on {world} GPU(s), AoS, h33-normalised",

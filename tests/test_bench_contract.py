@@ -60,3 +60,21 @@ def test_ours_arm_line(cuda):
     assert e["parity_vs_device_path"] == "bit-exact" and 0 < e["value"] < d["value"]
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["parity_gpu_vs_cpu"]["mismatching_elements"] == 0
+
+
+@pytest.mark.gpu
+def test_ours_arm_legs_for_the_other_configs(cuda):
+    """The `configs` legs (BASELINE configs[2..4]) at test sizes: RANSAC with its per-part breakdown and
+    oracle parity, rect strong, SKS f64 with the accuracy tier -- the same code path the full-size run takes."""
+    d = run_bench("--steps", "3", "--warmup", "3", "--log2n", "20", "--cpu-log2n", "16", "--no-gpu-baseline",
+                  "--force-legs", "--leg-log2n", "20", "--pairs", "16", "--points", "512", "--hyps", "2048",
+                  "--sustained-s", "0.2", "--ransac-cpu-evals", "2e6", "--e2e-steps", "3")
+    c = d["configs"]
+    r = c["ransac"]
+    assert r["parity"]["keys_equal_cpu_oracle"] is True and r["roofline"]["bound"] == "fp32"
+    assert set(r["breakdown"]) >= {"zero_keys_ms", "score_kernel_ms", "reduce_incl_wait_for_slowest_rank_ms", "finalize_ms"}
+    assert c["rect_2p28_strong"]["quadruples_per_gpu"] == 1 << 20 and c["rect_2p28_strong"]["scaling"] == "strong"
+    a = c["sks_f64_2p25"]["accuracy_tier"]
+    assert a["mismatching_elements_vs_runKernel_SKS_double"] == 0 and a["reprojection_px"]["p99"] < 1e-9
+    assert d["sustained"]["launches"] >= 200 and d["clocks"]["samples"] >= 5
+    assert d["e2e"]["pageable"]["parity_vs_device_path"] == "bit-exact" and d["e2e"]["link"]["h2d_GBps"] > 5
