@@ -14,11 +14,14 @@
 //   (division-free forward transfer error |proj(x) - X|^2 < thr^2, both sides
 //   multiplied by (w/thr)^2; the threshold is folded into the operands once per
 //   hypothesis and once per match, which leaves 11 FP32 operations per hypothesis
-//   x match instead of 12).  On the GPU "acc < 0" is read off the sign bit and
-//   added to the count with one integer instruction: acc is never -0 (e >= +0 and
-//   an exact cancellation rounds to +0) and a NaN acc is the canonical positive
-//   NaN on NVIDIA hardware, so the sign bit is exactly the IEEE comparison the
-//   oracle evaluates.
+//   x match instead of 12).  The integer scorers (MODE 0-2) read "acc < 0" off the
+//   sign bit and add it to the count with one LEA.HI: acc is never -0 (e >= +0 and
+//   an exact cancellation rounds to +0) and a NaN acc is the canonical positive NaN
+//   on NVIDIA hardware, so the sign bit is exactly the IEEE comparison the oracle
+//   evaluates.  The default scorer (MODE 3) keeps the count on the FP32 pipe:
+//   cnt = fma_rd(acc, 2^-149, cnt) steps a float counter down by exactly one ulp
+//   when acc < 0 (see ransac_inlier2_fp) -- one packed FFMA2.RM per two evaluations
+//   where the integer form needs two LEA.HI at two issue cycles each.
 //
 // Mapping: a CTA owns one image pair and a contiguous chunk of hypothesis ids.
 // The pair's correspondences (x,y,X,Y) are pulled into shared memory once by
@@ -26,11 +29,12 @@
 // pairs; every thread then carries HPT hypotheses in registers and walks the
 // tile with warp-uniform (broadcast) 16-byte shared loads, scoring two matches
 // per instruction with sm_100a's packed FFMA2 / FMUL2, so the inner loop is pure
-// FP32 pipe work: 10 packed FP32 + 2 FFMA + 2 LEA.HI per two hypothesis x match
-// evaluations.  The best (count, lowest id) is reduced with warp shuffles, then
-// one 64-bit atomicMax per CTA.  Bound: FP32 pipe, more precisely its register
-// operand bandwidth (tools/ubench/fma_peak.cu: an FFMA2 reading three fresh
-// register pairs issues at 2/3 rate), not HBM.
+// FP32 pipe work: 12 packed instructions per two hypothesis x match evaluations.
+// The best (count, lowest id) is reduced with warp shuffles, then one 64-bit
+// atomicMax per CTA.  Bound: the FP32 pipe (ncu: 93 % busy) together with the
+// register file's read bandwidth (two operands per cycle per scheduler:
+// tools/ubench/count_ops.cu, a packed FMA that needs a third register from one
+// bank takes three cycles instead of two), not HBM.
 #pragma once
 #include <cstdint>
 
