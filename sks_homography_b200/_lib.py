@@ -70,6 +70,8 @@ _SIGS = {
     "sks_host_set_chunk_bytes": (_int, [_i64]),
     "sks_host_alloc_pinned": (_int, [C.POINTER(_vp), _i64]),
     "sks_host_free_pinned": (_int, [_vp]),
+    "sks_host_register": (_int, [_vp, _i64]),
+    "sks_host_unregister": (_int, [_vp]),
     "sks_cuda_gather_samples_f32": (_int, [_vp, _u32, _vp, _u64, _vp, _vp, _i64, _int, _i64, _vp]),
     "sks_cuda_gather_samples_f64": (_int, [_vp, _u32, _vp, _u64, _vp, _vp, _i64, _int, _i64, _vp]),
     "sks_cuda_gather_aca_f32": (_int, [_vp, _u32, _vp, _u64, _vp, _i64, _int, _i64, _int, _vp, _vp]),

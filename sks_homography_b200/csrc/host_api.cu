@@ -733,6 +733,30 @@ int sks_host_free_pinned(void* ptr)
     return e == cudaSuccess ? SKS_OK : (int)e;
 }
 
+// Pin a buffer the caller already owns (a std::vector's storage, a numpy array): afterwards the
+// host-pointer entry points DMA from / into it directly instead of staging through the pinned ring.
+int sks_host_register(void* ptr, int64_t bytes)
+{
+    if (ptr == nullptr || bytes <= 0) return SKS_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return SKS_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SKS_ERR_NO_DEVICE : (int)e;
+    }
+    return SKS_OK;
+}
+int sks_host_unregister(void* ptr)
+{
+    if (ptr == nullptr) return SKS_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess ? SKS_OK : (int)e;
+}
+
 int sks_host_set_chunk_bytes(int64_t bytes_per_input_array)
 {
     if (bytes_per_input_array < (64 << 10) || bytes_per_input_array > (1ll << 30)) return SKS_ERR_INVALID_ARG;
