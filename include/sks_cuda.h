@@ -391,6 +391,12 @@ int sks_cuda_set_tuning(int small_tile, int stages, int ctas_per_sm);
  * the FP32 pipe by a directed-rounding FFMA2 -- all four give the same bits),
  * bits 2.. = CTA size (0: 256, 1: 384, 2: 512 threads). */
 int sks_cuda_set_ransac_tuning(int hyps_per_thread, int rounds_per_cta, int packed);
+/* The launch plan of the RANSAC scorer, exported for tests (pure host arithmetic, no GPU): the
+ * number of hypothesis ids one CTA scores -- rounds * threads * hyps_per_thread with rounds the
+ * tuning value halved down to 1, whichever minimises (waves of resident_ctas CTAs) x (rounds +
+ * 0.03): all CTAs of a launch take the same time, so a grid of 4.6 waves costs 5. */
+uint32_t sks_cuda_ransac_chunk_plan(int64_t n_pairs, uint32_t hyp_count, int threads,
+                                    int hyps_per_thread, int max_rounds, int resident_ctas);
 int sks_cuda_shutdown(void);
 
 #ifdef __cplusplus

@@ -105,6 +105,7 @@ _SIGS = {
     "sks_cuda_get_variant": (_int, []),
     "sks_cuda_set_tuning": (_int, [_int, _int, _int]),
     "sks_cuda_set_ransac_tuning": (_int, [_int, _int, _int]),
+    "sks_cuda_ransac_chunk_plan": (_u32, [_i64, _u32, _int, _int, _int, _int]),
     "sks_cuda_shutdown": (_int, []),
 }
 

@@ -472,6 +472,30 @@ int sks_cuda_curand_mrg32k3a_u32(uint32_t* out, int64_t n, uint64_t seed, void* 
     return finish_launch();
 }
 
+// Hypothesis ids per CTA.  Pure host arithmetic, exported so that it can be tested without a GPU.
+uint32_t sks_cuda_ransac_chunk_plan(int64_t n_pairs, uint32_t hyp_count, int threads, int hyps_per_thread,
+                                    int max_rounds, int resident_ctas)
+{
+    const uint32_t round = (uint32_t)threads * (uint32_t)hyps_per_thread;
+    if (max_rounds < 1) max_rounds = 1;
+    const double slots = resident_ctas > 0 ? (double)resident_ctas : 1.0;
+    uint32_t chunk = round * (uint32_t)max_rounds;
+    double best_cost = 0;
+    for (uint32_t r = (uint32_t)max_rounds, first = 1; r >= 1; r /= 2, first = 0) {
+        const double ctas = (double)(((uint64_t)hyp_count + (uint64_t)r * round - 1) / ((uint64_t)r * round)) *
+                            (double)n_pairs;
+        double waves = (double)(int64_t)((ctas + slots - 1) / slots);
+        if (waves < 1) waves = 1;
+        const double cost = waves * ((double)r + 0.03);
+        if (first || cost < best_cost * 0.995) {     // prefer more rounds per CTA unless it pays clearly
+            best_cost = cost;
+            chunk = r * round;
+        }
+        if (r == 1) break;
+    }
+    return chunk;
+}
+
 int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t n_pairs, int32_t n_pts,
                                   const uint32_t* samples, uint32_t hyp_stride, uint32_t hyp_begin,
                                   uint32_t hyp_count, uint64_t seed, float thr2,
@@ -509,24 +533,12 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
     // 5 x 2.6 ms).  Pick the rounds per CTA -- the tuning value, halved down to 1 -- that
     // minimises waves x (rounds + fixed cost), the fixed cost being the tile load and re-layout
     // (~10 us against ~330 us per round at 4096 matches, i.e. ~0.03 rounds).
-    const uint32_t round = (uint32_t)threads * (uint32_t)hpt;
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
-    const double slots = (double)dev.sms * occ;
-    uint32_t chunk = round * (uint32_t)t_tuning.ransac_rounds;
-    double best_cost = 0;
-    for (uint32_t r = (uint32_t)t_tuning.ransac_rounds, first = 1; r >= 1; r /= 2, first = 0) {
-        const double ctas = (double)((hyp_count + r * round - 1) / (r * round)) * (double)n_pairs;
-        const double waves = (double)(int64_t)((ctas + slots - 1) / slots);
-        const double cost = (waves < 1 ? 1 : waves) * ((double)r + 0.03);
-        if (first || cost < best_cost * 0.995) {     // prefer more rounds per CTA unless it pays clearly
-            best_cost = cost;
-            chunk = r * round;
-        }
-        if (r == 1) break;
-    }
+    const uint32_t chunk = sks_cuda_ransac_chunk_plan(n_pairs, hyp_count, threads, hpt, t_tuning.ransac_rounds,
+                                                      dev.sms * occ);
     const unsigned chunks = (hyp_count + chunk - 1) / chunk;
     // grid.y is limited to 65535: larger batches go out in blocks of pairs; the kernel
     // takes its pair id from pair_base + blockIdx.y so sampling does not depend on blocking

@@ -122,3 +122,23 @@ def test_tuning_knobs_are_per_thread(sks):
         assert sks.c.sks_cuda_get_variant() == 2
     finally:
         sks.c.sks_cuda_set_variant(0)
+
+
+def test_ransac_launch_plan_fills_whole_waves(sks):
+    """BASELINE configs[4] on 1/2/4/8 ranks (148 SMs x 3 resident CTAs): the plan halves the rounds
+    per CTA exactly where a partial last wave would cost more than the extra tile loads."""
+    plan = sks.c.sks_cuda_ransac_chunk_plan
+    slots, round_ = 148 * 3, 256 * 2
+    want_rounds = {1: 8, 2: 4, 4: 2, 8: 1}
+    for world, rounds in want_rounds.items():
+        chunk = plan(1024, 65536 // world, 256, 2, 8, slots)
+        assert chunk == rounds * round_, (world, chunk)
+        ctas = -(-(65536 // world) // chunk) * 1024
+        waves = ctas / slots
+        assert -(-ctas // slots) / waves < 1.01               # < 1 % lost to the partial last wave
+    # few CTAs: one wave whatever the split -> the finest one (most parallelism)
+    assert plan(4, 2048, 256, 2, 8, slots) == round_
+    # always a multiple of a round, never zero, covers odd counts
+    for hyp in (1, 511, 513, 70001):
+        c = plan(3, hyp, 384, 4, 3, slots)
+        assert c > 0 and c % (384 * 4) == 0
