@@ -61,7 +61,7 @@ def gather(x):
         dist.all_gather(out, t)
     else:
         out = [t]
-    return [round(float(o.item()), 1) for o in out]
+    return [round(float(o.item()), 3) for o in out]
 
 
 res = {"world": world, "buffer_GiB": 1}
@@ -88,6 +88,48 @@ def bidir():
 
 
 res["bidir_h2d_GBps"] = gather(rate(bidir))
+# the e2e pipeline's traffic mix (64 B in : 36 B out per homography), two ways: both directions at once on
+# two streams (what the pipeline does), or globally ALIGNED phases -- every rank copies in, barrier, every
+# rank copies out, barrier -- so that host->device and device->host traffic never share the host
+IN, OUT = 64 << 20, 36 << 20
+hi, ho = h[:IN], h2[:OUT]
+di, do = d[:IN], d2[:OUT]
+
+
+def mixed(aligned, cycles=24):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for _ in range(cycles):
+        if aligned:
+            di.copy_(hi, non_blocking=True)
+            barrier()
+            ho.copy_(do, non_blocking=True)
+            barrier()
+        else:
+            di.copy_(hi, non_blocking=True)
+            with torch.cuda.stream(s2):
+                ho.copy_(do, non_blocking=True)
+            torch.cuda.synchronize()
+    barrier()
+    el = time.perf_counter() - t0
+    return cycles * (IN / 64) / el / 1e9          # G homographies/s this rank could feed
+
+
+res["mixed_overlapped_GHps"] = gather(round(mixed(False), 4))
+res["mixed_aligned_GHps"] = gather(round(mixed(True), 4))
+d2h_rate = []
+s3 = torch.cuda.Stream()
+
+
+def bidir_d2h():
+    with torch.cuda.stream(s3):
+        d.copy_(h, non_blocking=True)
+    h2.copy_(d2, non_blocking=True)
+
+
+res["bidir_d2h_GBps"] = gather(rate(bidir_d2h))
+res["together_d2h_GBps"] = gather(rate(lambda: h2.copy_(d2, non_blocking=True)))
 # transparent-hugepage-backed host memory, registered with CUDA
 try:
     mm = mmap.mmap(-1, N, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
@@ -116,7 +158,10 @@ if rank == 0:
         res["host"] = {"cpus": os.cpu_count(), "numa_nodes": len([x for x in os.listdir("/sys/devices/system/node") if x.startswith("node")])}
     except Exception:
         pass
-    for k in ("alone_GBps", "together_GBps", "staggered_GBps", "bidir_h2d_GBps", "hugepages_GBps"):
+    for k in ("mixed_overlapped_GHps", "mixed_aligned_GHps"):
+        res[k.replace("_GHps", "_sum_GHps")] = round(sum(res[k]), 3)
+    for k in ("alone_GBps", "together_GBps", "staggered_GBps", "bidir_h2d_GBps", "bidir_d2h_GBps", "together_d2h_GBps",
+              "hugepages_GBps"):
         if k in res:
             res[k.replace("_GBps", "_sum_GBps")] = round(sum(res[k]), 1)
     print(json.dumps(res))
