@@ -716,7 +716,9 @@ def measure_ransac(cx, steps, warmup, shard="hypotheses", peer_reduce=False, bre
             ev[4].record()
             seg.append(ev)
 
+    sampler = ClockSampler(cx.local) if rank == 0 else None      # SM clock / power DURING the scoring steps
     ms_per_step, per, launches = timed_steps(cx, step, steps, warmup)
+    clocks = sampler.stop() if sampler else None
     value = P * n_hyp / (ms_per_step * 1e-3)
 
     parts = None
@@ -865,7 +867,7 @@ def measure_ransac(cx, steps, warmup, shard="hypotheses", peer_reduce=False, bre
                    "thr2": thr2, "seed": args.seed,
                    "l2": "compute-bound; matches (64 KiB/pair) live in shared memory"},
         "roofline": roofline, "breakdown": parts, "parity": parity, "e2e": e2e, "cpu_baseline": cpu,
-        "gpu_launches": launches,
+        "gpu_launches": launches, "clocks": clocks,
         "mean_inlier_fraction_of_winner": float(res["cnt"].float().mean().item()) / n_pts,
         "peer_reduce_timed_out": reducer.timed_out() if reducer else None,
     }
