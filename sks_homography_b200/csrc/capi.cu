@@ -512,16 +512,20 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
     if (n_pairs == 0 || hyp_count == 0) return SKS_OK;
     const int32_t tile_pts = n_pts < kRansacMaxTilePts ? n_pts : kRansacMaxTilePts;
     const int smem = ((tile_pts + 1) & ~1) * 16;
-    const int hpt = t_tuning.ransac_hpt;
+    const int hpt = t_tuning.ransac_hpt;                       // 2 or "4" (the HI instantiation)
     const int mode = t_tuning.ransac_packed;
     const int threads = t_tuning.ransac_threads;
     using Kern = void (*)(const float4*, int64_t, int32_t, int32_t, const uint32_t*, uint32_t, uint32_t,
                           uint32_t, uint32_t, uint64_t, float, unsigned long long*, int64_t);
+#ifndef SKS_RANSAC_HPT_HI
+#define SKS_RANSAC_HPT_HI 4      // the "4 hypotheses per thread" instantiation (sweep builds try 3)
+#endif
+    constexpr int HI = SKS_RANSAC_HPT_HI, HI2 = (SKS_RANSAC_HPT_HI % 2) ? 2 : SKS_RANSAC_HPT_HI;
 #define SKS_RANSAC_PICK(T)                                                                        \
-    (mode == 3 ? (hpt == 4 ? k_ransac_aca<4, 3, T> : k_ransac_aca<2, 3, T>)                       \
-     : mode == 2 ? (hpt == 4 ? k_ransac_aca<4, 2, T> : k_ransac_aca<2, 2, T>)                     \
-     : mode == 1 ? (hpt == 4 ? k_ransac_aca<4, 1, T> : k_ransac_aca<2, 1, T>)                     \
-                 : (hpt == 4 ? k_ransac_aca<4, 0, T> : k_ransac_aca<2, 0, T>))
+    (mode == 3 ? (hpt == 4 ? k_ransac_aca<HI, 3, T> : k_ransac_aca<2, 3, T>)                      \
+     : mode == 2 ? (hpt == 4 ? k_ransac_aca<HI2, 2, T> : k_ransac_aca<2, 2, T>)                   \
+     : mode == 1 ? (hpt == 4 ? k_ransac_aca<HI, 1, T> : k_ransac_aca<2, 1, T>)                    \
+                 : (hpt == 4 ? k_ransac_aca<HI, 0, T> : k_ransac_aca<2, 0, T>))
     const Kern kern = threads == 512 ? SKS_RANSAC_PICK(512)
                     : threads == 384 ? SKS_RANSAC_PICK(384) : SKS_RANSAC_PICK(256);
 #undef SKS_RANSAC_PICK
@@ -537,7 +541,7 @@ int sks_cuda_ransac_aca_shard_f32(const float* corr, int64_t pair_begin, int64_t
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
-    const uint32_t chunk = sks_cuda_ransac_chunk_plan(n_pairs, hyp_count, threads, hpt, t_tuning.ransac_rounds,
+    const uint32_t chunk = sks_cuda_ransac_chunk_plan(n_pairs, hyp_count, threads, hpt == 4 ? HI : 2, t_tuning.ransac_rounds,
                                                       dev.sms * occ);
     const unsigned chunks = (hyp_count + chunk - 1) / chunk;
     // grid.y is limited to 65535: larger batches go out in blocks of pairs; the kernel

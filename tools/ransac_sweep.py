@@ -11,9 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "tools", "_variants")
 CAP2 = "-DSKS_RANSAC_MIN_CTAS(T)=2"
-VARIANTS = {"rs_base": [], "rs_fp_joint_cap2": [CAP2, "-DSKS_RANSAC_FP_JOINT=1"],
-            "rs_fp_joint_cap2_u4": [CAP2, "-DSKS_RANSAC_FP_JOINT=1", "-DSKS_RANSAC_FP_UNROLL=4"],
-            "rs_fp_cap2": [CAP2], "rs_fp_joint_u1": ["-DSKS_RANSAC_FP_JOINT=1", "-DSKS_RANSAC_FP_UNROLL=1"]}
+VARIANTS = {"rs_base": [], "rs_fp_h3": ["-DSKS_RANSAC_HPT_HI=3"], "rs_fp_h3_u1": ["-DSKS_RANSAC_HPT_HI=3", "-DSKS_RANSAC_FP_UNROLL=1"],
+            "rs_fp_h3_u3": ["-DSKS_RANSAC_HPT_HI=3", "-DSKS_RANSAC_FP_UNROLL=3"]}
 EXTRA = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
 for e in EXTRA:                      # --variant=tag:-DX=1,-DY=2
     tag, defs = e.split(":", 1)
@@ -46,7 +45,7 @@ P, n_pts, n_hyp = 256, 4096, 65536
 corr = api.synth_corr(P, n_pts, seed=11, device=dev)
 ref = api.ransac_keys(corr, n_hyp, 11, 2.25)
 st = torch.cuda.current_stream().cuda_stream
-CONFIGS = [(3, 2, 0), (3, 4, 0), (3, 2, 1)]
+CONFIGS = [(3, 2, 0), (3, 4, 0), (3, 4, 1)]
 for path in sorted(glob.glob(os.path.join(VDIR, "libsks_cuda_rs_*.so"))):
     L = _lib.SksCuda(path)
     for mode, hpt, thr in CONFIGS:
