@@ -174,6 +174,9 @@ int sks_host_set_chunk_bytes(int64_t bytes_per_input_array);
  * ring, bit 1 = out of it into the caller's result buffer; 0 = plain memcpy both ways.
  * A tuning knob for measurements; every setting gives the same bytes. */
 int sks_host_set_staging_copy(int non_temporal);
+/* Worker threads one staging copy is spread over (1..64; 0 = default = three quarters of the pool of
+ * min(16, cores) workers). */
+int sks_host_set_staging_threads(int threads_per_copy);
 /* pinned host allocation helpers for callers that want the zero-staging path */
 int sks_host_alloc_pinned(void **ptr, int64_t bytes);
 int sks_host_free_pinned(void *ptr);

@@ -67,6 +67,7 @@ _SIGS = {
     "sks_cuda_ransac_aca_multi_f32": (_int, [_vp, _i64, _i32, _vp, _u32, _u64, _f32, _int, _vp, _vp, _vp, _vp, _vp]),
     "sks_host_set_device_count": (_int, [_int]),
     "sks_host_set_staging_copy": (_int, [_int]),
+    "sks_host_set_staging_threads": (_int, [_int]),
     "sks_host_set_chunk_bytes": (_int, [_i64]),
     "sks_host_alloc_pinned": (_int, [C.POINTER(_vp), _i64]),
     "sks_host_free_pinned": (_int, [_vp]),

@@ -276,9 +276,19 @@ private:
     std::vector<std::thread> workers_;
 };
 
+// worker threads one staging copy is spread over (sks_host_set_staging_threads); 0 = three quarters of the
+// pool (12 of 16: measured best on a 16-vCPU B200 host, 0.65 vs 0.58 G H/s at 8 and 0.59 at 16 -- the in- and
+// out-stager copy at the same time and share the pool)
+std::atomic<int> g_copy_parts{0};
 void parallel_copy(void* dst, const void* src, size_t bytes, bool nt)
 {
-    CopyPool::get().copy(dst, src, bytes, 8, nt);
+    int parts = g_copy_parts.load();
+    if (parts <= 0) {
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        parts = (int)(std::min(16u, hw) * 3 / 4);
+        if (parts < 1) parts = 1;
+    }
+    CopyPool::get().copy(dst, src, bytes, (unsigned)parts, nt);
 }
 
 }  // namespace
@@ -768,6 +778,13 @@ int sks_host_set_staging_copy(int non_temporal)
 {
     if (non_temporal < 0 || non_temporal > 3) return SKS_ERR_INVALID_ARG;
     g_stream_copy.store(non_temporal);
+    return SKS_OK;
+}
+
+int sks_host_set_staging_threads(int threads_per_copy)
+{
+    if (threads_per_copy < 0 || threads_per_copy > 64) return SKS_ERR_INVALID_ARG;   // 0 = automatic
+    g_copy_parts.store(threads_per_copy);
     return SKS_OK;
 }
 

@@ -26,6 +26,11 @@ for nt in (3, 0, 1, 2, 3):
         ref = H.clone()
     print(f"pageable in/out, staging_copy={nt}: {n / tp / 1e9:.3f} G H/s  same={torch.equal(H.view(torch.int32), ref.view(torch.int32))}", flush=True)
 L.c.sks_host_set_staging_copy(3)
+for parts in (2, 4, 6, 8, 12, 16):
+    L.c.sks_host_set_staging_threads(parts)
+    tp = best(lambda: api.solve("aca", s, t, result=H))
+    print(f"pageable in/out, NT, {parts:2d} threads per copy: {n / tp / 1e9:.3f} G H/s", flush=True)
+L.c.sks_host_set_staging_threads(0)
 sp, tq, Hp = s.pin_memory(), t.pin_memory(), H.pin_memory()
 tp = best(lambda: api.solve("aca", sp, tq, result=Hp))
 print(f"pinned in/out  : {n / tp / 1e9:.3f} G H/s")
