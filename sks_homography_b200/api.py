@@ -25,8 +25,51 @@ from ._lib import FLAG_NORMALIZE, LAYOUT_AOS, LAYOUT_SOA, lib
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
 
 
+# Small batches (the deep-homography sizes, bs = 64 ... 4096) are call-overhead bound: one kernel of a
+# few microseconds behind ~20 us of Python.  The helpers below keep that layer thin: the raw stream handle
+# without building a torch.cuda.Stream object, and a device guard that does nothing when the tensor
+# already lives on the current device.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(t: torch.Tensor) -> int:
+    if _raw_stream is not None:
+        idx = t.device.index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_FN = {}
+
+
+def _entry(name: str):
+    """ctypes entry point by name, cached (attribute lookup on a CDLL is not free)."""
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib().c, name)
+    return fn
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` without its cost in the common case (already current)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = None
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _ptr(t):
@@ -70,10 +113,11 @@ def solve(solver: str, src: torch.Tensor, tar: torch.Tensor, result: torch.Tenso
     flags = FLAG_NORMALIZE if normalize else 0
     name = f"{solver}_{_SUFFIX[dtype]}"
     if src.is_cuda:
-        with torch.cuda.device(src.device):
-            fn = getattr(L.c, f"sks_cuda_{name}")
-            L.check(fn(_ptr(src), _ptr(tar), _ptr(result), n, lay, ld, flags, _ptr(degenerate),
-                       _stream_ptr(src)), f"sks_cuda_{name}")
+        with _on_device(src.device):
+            rc = _entry("sks_cuda_" + name)(src.data_ptr(), tar.data_ptr(), result.data_ptr(), n, lay, ld, flags,
+                                           _ptr(degenerate), _stream_ptr(src))
+            if rc:
+                L.check(rc, f"sks_cuda_{name}")
     else:
         if layout != "aos" or degenerate is not None:
             raise ValueError("host tensors: AoS layout without flag output only")
@@ -145,7 +189,7 @@ def aca_rect(tar: torch.Tensor, width: float, ratio: float, M_x: float = 0.0, M_
     flags = FLAG_NORMALIZE if normalize else 0
     name = f"aca_rect_{_SUFFIX[dtype]}"
     if tar.is_cuda:
-        with torch.cuda.device(tar.device):
+        with _on_device(tar.device):
             fn = getattr(L.c, f"sks_cuda_{name}")
             L.check(fn(_ptr(tar), _ptr(M), M_x, M_y, width, ratio, _ptr(result), n, lay, ld, flags,
                        _ptr(degenerate), _stream_ptr(tar)), f"sks_cuda_{name}")
@@ -182,7 +226,7 @@ def TensorACA_rect(bs: int, src: torch.Tensor, tar: torch.Tensor, scale, div) ->
         H = torch.empty((bs, 3, 3), dtype=tar.dtype, device=tar.device)
         on_dev = all(torch.is_tensor(x) and x.device == tar.device and x.dtype == tar.dtype and x.numel() == 1
                      for x in (scale, div))
-        with torch.cuda.device(tar.device):
+        with _on_device(tar.device):
             if on_dev:      # the reference's own calling convention: scale / div are device tensors; no sync
                 fn = getattr(L.c, f"sks_cuda_aca_rect_planar_dev_{_SUFFIX[tar.dtype]}")
                 L.check(fn(_ptr(tar), _ptr(src), _ptr(scale.contiguous()), _ptr(div.contiguous()), _ptr(H), bs, 0,
@@ -213,7 +257,7 @@ def synth_quads(n: int, seed: int = 11, dist: int = _lib.DIST_DEEP, dtype=torch.
     shape = (n, 8) if layout == "aos" else (8, n)
     src = torch.empty(shape, dtype=dtype, device=dev)
     tar = torch.empty(shape, dtype=dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         fn = getattr(L.c, f"sks_cuda_synth_quads_{_SUFFIX[dtype]}")
         L.check(fn(_ptr(src), _ptr(tar), begin, n, seed, dist,
                    LAYOUT_AOS if layout == "aos" else LAYOUT_SOA, n, _stream_ptr(src)),
@@ -226,7 +270,7 @@ def synth_corr(n_pairs: int, n_pts: int, seed: int = 11, inlier_permille: int = 
     L = lib()
     dev = torch.device(device)
     corr = torch.empty((n_pairs, n_pts, 4), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         L.check(L.c.sks_cuda_synth_corr_f32(_ptr(corr), pair_begin, n_pairs, n_pts, seed,
                                             inlier_permille, noise, _stream_ptr(corr)),
                 "sks_cuda_synth_corr_f32")
@@ -242,7 +286,7 @@ def gather_samples(pool: torch.Tensor, n: int, seed: int = 11, rand4: torch.Tens
     shape = (n, 8) if layout == "aos" else (8, n)
     src = torch.empty(shape, dtype=dtype, device=pool.device)
     tar = torch.empty(shape, dtype=dtype, device=pool.device)
-    with torch.cuda.device(pool.device):
+    with _on_device(pool.device):
         fn = getattr(L.c, f"sks_cuda_gather_samples_{_SUFFIX[dtype]}")
         L.check(fn(_ptr(pool), pool.shape[0], _ptr(rand4), seed, _ptr(src), _ptr(tar), n,
                    LAYOUT_AOS if layout == "aos" else LAYOUT_SOA, n, _stream_ptr(pool)),
@@ -259,7 +303,7 @@ def gather_solve(solver: str, pool: torch.Tensor, n: int, seed: int = 11,
     dtype = pool.dtype
     pool = pool.contiguous()
     H = torch.empty((n, 9) if layout == "aos" else (9, n), dtype=dtype, device=pool.device)
-    with torch.cuda.device(pool.device):
+    with _on_device(pool.device):
         fn = getattr(L.c, f"sks_cuda_gather_{solver}_{_SUFFIX[dtype]}")
         L.check(fn(_ptr(pool), pool.shape[0], _ptr(rand4), seed, _ptr(H), n,
                    LAYOUT_AOS if layout == "aos" else LAYOUT_SOA, n,
@@ -277,7 +321,7 @@ def warp_grid(H: torch.Tensor, gw: int, gh: int, x0: float = 0.0, y0: float = 0.
     n = H.numel() // 9
     if out is None:
         out = torch.empty((n, gh, gw, 2), dtype=torch.float32, device=H.device)
-    with torch.cuda.device(H.device):
+    with _on_device(H.device):
         L.check(L.c.sks_cuda_warp_grid_f32(_ptr(H), n, x0, y0, dx, dy, gw, gh, _ptr(out), _stream_ptr(H)),
                 "sks_cuda_warp_grid_f32")
     return out
@@ -296,7 +340,7 @@ def aca_rect_warp_grid(tar: torch.Tensor, width: float, ratio: float, gw: int, g
         M = M.contiguous()
     if out is None:
         out = torch.empty((n, gh, gw, 2), dtype=torch.float32, device=tar.device)
-    with torch.cuda.device(tar.device):
+    with _on_device(tar.device):
         L.check(L.c.sks_cuda_aca_rect_warp_grid_f32(_ptr(tar), _ptr(M), M_x, M_y, width, ratio, n, x0, y0,
                                                     dx, dy, gw, gh, _ptr(out), _stream_ptr(tar)),
                 "sks_cuda_aca_rect_warp_grid_f32")
@@ -312,7 +356,7 @@ def curand_mrg32k3a(n: int, seed: int = 11, device="cuda", out: torch.Tensor | N
         out = torch.empty(n, dtype=torch.int32, device=torch.device(device))
     elif out.numel() != n or out.dtype != torch.int32 or not out.is_contiguous():
         raise ValueError("out must be a contiguous int32 tensor of n elements")
-    with torch.cuda.device(out.device):
+    with _on_device(out.device):
         L.check(L.c.sks_cuda_curand_mrg32k3a_u32(_ptr(out), n, seed, _stream_ptr(out)),
                 "sks_cuda_curand_mrg32k3a_u32")
     return out
@@ -348,7 +392,7 @@ def ransac_keys(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float,
     hyp_count = n_hyp - hyp_begin if hyp_count is None else hyp_count
     if out is None:
         out = torch.zeros(P, dtype=torch.int64, device=corr.device)
-    with torch.cuda.device(corr.device):
+    with _on_device(corr.device):
         L.check(L.c.sks_cuda_ransac_aca_shard_f32(_ptr(corr), pair_begin, P, n_pts, _ptr(samples), n_hyp,
                                                   hyp_begin, hyp_count, seed, thr2, _ptr(out),
                                                   _stream_ptr(corr)),
@@ -395,7 +439,7 @@ def ransac_multi(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, ngpu: i
     H = torch.empty((P, 9), dtype=torch.float32, device=dev) if finalize else None
     cnt = torch.empty(P, dtype=torch.int32, device=dev) if finalize else None
     mask = torch.empty((P, n_pts), dtype=torch.uint8, device=dev) if (finalize and want_mask) else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         L.check(L.c.sks_cuda_ransac_aca_multi_f32(_ptr(corr), P, n_pts, _ptr(samples), n_hyp, seed, thr2, ngpu,
                                                   _ptr(keys), _ptr(H), _ptr(cnt), _ptr(mask), _stream_ptr(corr)),
                 "sks_cuda_ransac_aca_multi_f32")
@@ -413,7 +457,7 @@ def ransac_finalize(corr: torch.Tensor, n_hyp: int, seed: int, thr2: float, keys
     H = torch.empty((P, 9), dtype=torch.float32, device=corr.device)
     cnt = torch.empty(P, dtype=torch.int32, device=corr.device)
     mask = torch.empty((P, n_pts), dtype=torch.uint8, device=corr.device) if want_mask else None
-    with torch.cuda.device(corr.device):
+    with _on_device(corr.device):
         L.check(L.c.sks_cuda_ransac_finalize_shard_f32(_ptr(corr), pair_begin, P, n_pts, _ptr(samples), n_hyp,
                                                  seed, thr2, _ptr(keys), _ptr(H), _ptr(cnt), _ptr(mask),
                                                  _stream_ptr(corr)),
@@ -428,7 +472,7 @@ def ransac_score(corr: torch.Tensor, H: torch.Tensor, thr2: float, want_mask: bo
     P, n_pts, _ = corr.shape
     cnt = torch.empty(P, dtype=torch.int32, device=corr.device)
     mask = torch.empty((P, n_pts), dtype=torch.uint8, device=corr.device) if want_mask else None
-    with torch.cuda.device(corr.device):
+    with _on_device(corr.device):
         L.check(L.c.sks_cuda_ransac_score_f32(_ptr(corr), P, n_pts, _ptr(H), thr2, _ptr(cnt), _ptr(mask),
                                               _stream_ptr(corr)), "sks_cuda_ransac_score_f32")
     return cnt, mask
@@ -458,7 +502,7 @@ def ransac_refit(corr: torch.Tensor, mask: torch.Tensor, H: torch.Tensor):
     P, n_pts, _ = corr.shape
     out = torch.empty((P, 9), dtype=torch.float32, device=corr.device)
     used = torch.empty(P, dtype=torch.int32, device=corr.device)
-    with torch.cuda.device(corr.device):
+    with _on_device(corr.device):
         L.check(L.c.sks_cuda_ransac_refit_f32(_ptr(corr), P, n_pts, _ptr(mask), _ptr(H), _ptr(out), _ptr(used),
                                               _stream_ptr(corr)), "sks_cuda_ransac_refit_f32")
     return out, used
