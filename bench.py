@@ -650,7 +650,19 @@ def reference_torch_eager(api, dev, log2ns=(6, 10, 14, 20, 22, 24)):
             H_our = api.TensorACA_rect(bs, src_new, tar_new, scale, div)
             t_our = _event_ms(lambda: api.TensorACA_rect(bs, src_new, tar_new, scale, div), iters)
             same_rect = bool(torch.equal(H_ref.reshape(bs, 9).view(torch.int32), H_our.reshape(bs, 9).view(torch.int32)))
+            graph_us = None
+            if log2n < 16:      # launch-bound sizes: the same call captured once in a CUDA graph and replayed
+                try:
+                    torch.cuda.synchronize()
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        api.TensorACA_rect(bs, src_new, tar_new, scale, div)
+                    graph_us = 1e3 * _event_ms(gr.replay, iters)
+                    del gr
+                except Exception as e:
+                    graph_us = f"{type(e).__name__}: {e}"[:80]
             out["rows"].append({"fn": "TensorACA_rect", "bs": bs, "reference_us": 1e3 * t_ref, "ours_us": 1e3 * t_our,
+                                "ours_cuda_graph_replay_us": graph_us,
                                 "speedup": t_ref / t_our, "reference_GHps": bs / t_ref / 1e6, "ours_GHps": bs / t_our / 1e6,
                                 "ours_GBps_tensor_layout": bs * (48 + 36) / t_our / 1e6, "bit_identical": same_rect})
             del H_ref, H_our

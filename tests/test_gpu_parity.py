@@ -579,3 +579,38 @@ def test_registering_a_caller_owned_buffer_takes_the_direct_dma_path(api, sks, o
     finally:
         for a, _ in bufs:
             sks.c.sks_host_unregister(a.ctypes.data)
+
+
+def test_calls_are_cuda_graph_capturable(api, oracle, cuda):
+    """The device-pointer entry points only enqueue on the current stream (no sync, no allocation in the
+    library), so a launch-bound training loop can capture them in a CUDA graph and replay it:
+    TensorACA_rect with device-resident scale / div and the general solver, replayed on new inputs."""
+    bs = 256
+    g = torch.Generator(device="cpu").manual_seed(3)
+    def make():
+        src = torch.randint(10, 30, (bs, 2), generator=g).float().unsqueeze(1).repeat(1, 4, 1)
+        src[:, 1, 0] += 128; src[:, 2, 1] += 128; src[:, 3, 0] += 128; src[:, 3, 1] += 128
+        tar = src + torch.randint(0, 32, (bs, 4, 2), generator=g).float()
+        return src, tar
+    def planar(a):
+        return torch.cat((a.transpose(1, 2), torch.ones((bs, 1, 4))), dim=1).contiguous()
+    src, tar = make()
+    s34, t34 = planar(src).to(cuda), planar(tar).to(cuda)
+    sq, tq = src.reshape(bs, 8).contiguous().to(cuda), tar.reshape(bs, 8).contiguous().to(cuda)
+    scale = (s34[0, 0, 1:2] - s34[0, 0, 0:1]).clone()
+    div = (scale / (s34[0, 1, 2:3] - s34[0, 1, 0:1])).clone()
+    api.TensorACA_rect(bs, s34, t34, scale, div); api.solve("aca", sq, tq)      # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        H_rect = api.TensorACA_rect(bs, s34, t34, scale, div)
+        H_aca = api.solve("aca", sq, tq)
+    for _ in range(3):                                    # replay on fresh inputs copied into the static buffers
+        src, tar = make()
+        s34.copy_(planar(src)); t34.copy_(planar(tar)); sq.copy_(src.reshape(bs, 8)); tq.copy_(tar.reshape(bs, 8))
+        graph.replay()
+        torch.cuda.synchronize()
+        want = oracle.solve("aca", src.reshape(bs, 8).numpy(), tar.reshape(bs, 8).numpy())
+        assert_same_bits(H_aca.cpu().numpy(), want, "graph replay, general solver")
+        eager = api.TensorACA_rect(bs, s34, t34, scale, div)
+        assert torch.equal(H_rect.view(torch.int32), eager.view(torch.int32))
