@@ -66,7 +66,7 @@ def test_ours_arm_line(cuda):
 def test_ours_arm_legs_for_the_other_configs(cuda):
     """The `configs` legs (BASELINE configs[2..4]) at test sizes: RANSAC with its per-part breakdown and
     oracle parity, rect strong, SKS f64 with the accuracy tier -- the same code path the full-size run takes."""
-    d = run_bench("--steps", "3", "--warmup", "3", "--log2n", "20", "--cpu-log2n", "16", "--no-gpu-baseline",
+    d = run_bench("--steps", "3", "--warmup", "3", "--log2n", "20", "--cpu-log2n", "16",
                   "--force-legs", "--leg-log2n", "20", "--pairs", "16", "--points", "512", "--hyps", "2048",
                   "--sustained-s", "0.2", "--ransac-cpu-evals", "2e6", "--e2e-steps", "3")
     c = d["configs"]
@@ -78,3 +78,12 @@ def test_ours_arm_legs_for_the_other_configs(cuda):
     assert a["mismatching_elements_vs_runKernel_SKS_double"] == 0 and a["reprojection_px"]["p99"] < 1e-9
     assert d["sustained"]["launches"] >= 200 and d["clocks"]["samples"] >= 5
     assert d["e2e"]["pageable"]["parity_vs_device_path"] == "bit-exact" and d["e2e"]["link"]["h2d_GBps"] > 5
+    # same-box comparators: the reference's CUDA kernels and its torch-eager functions (both staged into
+    # oracle/_ref at build time; "unavailable" where they were not)
+    g = d["gpu_baseline"]
+    if "rows" in g:
+        assert all(r["ours_us"] > 0 and r["reference_us"] > 0 for r in g["rows"])
+    te = g.get("torch_eager_fp32", {})
+    if "rows" in te:
+        good = [r for r in te["rows"] if "error" not in r]
+        assert good and all(r["bit_identical"] for r in good) and all(r["speedup"] > 1 for r in good)
