@@ -90,3 +90,21 @@ def test_multi_rank_nccl_and_peer_reduce_under_torchrun(tmp_path):
                           os.path.join(ROOT, "tests", "tools", "multi_rank_check.py")],
                          capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "MULTI_RANK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(N_GPU < 2, reason="needs >= 2 GPUs")
+def test_tensors_on_a_non_current_device(api, oracle):
+    """A tensor on cuda:1 while cuda:0 is current: the call switches device for the launch (and the
+    stream handle it passes is that device's current stream) and switches back."""
+    assert torch.cuda.current_device() == 0
+    d1 = torch.device("cuda", 1)
+    s, t = oracle.synth_quads(0, 5000, 4, 1, np.float32)
+    H = api.solve("aca", torch.from_numpy(s).to(d1), torch.from_numpy(t).to(d1))
+    assert H.device == d1 and torch.cuda.current_device() == 0
+    want = oracle.solve("aca", s, t)
+    got = H.cpu().numpy()
+    assert np.array_equal(np.nan_to_num(got).view(np.uint32), np.nan_to_num(want).view(np.uint32))
+    corr = api.synth_corr(3, 600, seed=2, device=d1)
+    keys = api.ransac_keys(corr, 256, 3, 2.25)
+    assert keys.device == d1 and torch.cuda.current_device() == 0
+    assert np.array_equal(keys.cpu().numpy().view(np.uint64), oracle.ransac(corr.cpu().numpy(), 256, 3, 2.25))
