@@ -108,3 +108,27 @@ def test_tensors_on_a_non_current_device(api, oracle):
     keys = api.ransac_keys(corr, 256, 3, 2.25)
     assert keys.device == d1 and torch.cuda.current_device() == 0
     assert np.array_equal(keys.cpu().numpy().view(np.uint64), oracle.ransac(corr.cpu().numpy(), 256, 3, 2.25))
+
+
+def test_multi_entry_edge_cases(api, sks, oracle, cuda):
+    """ngpu larger than the box or than the hypothesis count is clamped, an empty batch is a no-op,
+    the finalize step is optional, invalid arguments are rejected -- on any number of GPUs."""
+    corr = api.synth_corr(3, 300, seed=4, device=cuda)
+    want = oracle.ransac(corr.cpu().numpy(), 5, 2, 2.25)
+    for ngpu in (0, 1, 99):
+        H, cnt, mask, keys = api.ransac_multi(corr, 5, 2, 2.25, ngpu=ngpu)
+        assert np.array_equal(keys.cpu().numpy().view(np.uint64), want)
+    H, cnt, mask, keys = api.ransac_multi(corr, 1, 2, 2.25, ngpu=0)                 # one hypothesis: one device
+    assert np.array_equal(keys.cpu().numpy().view(np.uint64), oracle.ransac(corr.cpu().numpy(), 1, 2, 2.25))
+    H, cnt, mask, keys = api.ransac_multi(corr, 5, 2, 2.25, ngpu=0, finalize=False)
+    assert H is None and cnt is None and np.array_equal(keys.cpu().numpy().view(np.uint64), want)
+    st = torch.cuda.current_stream(cuda).cuda_stream
+    k = torch.zeros(3, dtype=torch.int64, device=cuda)
+    f = sks.c.sks_cuda_ransac_aca_multi_f32
+    assert f(corr.data_ptr(), 0, 300, None, 5, 2, 2.25, 0, k.data_ptr(), None, None, None, st) == 0      # empty batch
+    assert f(corr.data_ptr(), 3, 300, None, 0, 2, 2.25, 0, k.data_ptr(), None, None, None, st) == -1     # no hypotheses
+    assert f(corr.data_ptr(), 3, 300, None, 5, 2, 2.25, -1, k.data_ptr(), None, None, None, st) == -1    # ngpu < 0
+    assert f(None, 3, 300, None, 5, 2, 2.25, 0, k.data_ptr(), None, None, None, st) == -1
+    h = sks.c.sks_host_ransac_aca_multi_f32
+    Hh = torch.empty((3, 9))
+    assert h(corr.cpu().data_ptr(), 3, 300, None, 0, 2, 2.25, 0, Hh.data_ptr(), None, None, None) == -1
