@@ -59,6 +59,43 @@ __global__ void __launch_bounds__(256) k_mix(const C32* a, const C32* b, C16* h,
         if (base + c < n * 36 / 16) st16(h + base + c, *reinterpret_cast<C16*>(stage + 4 * c));
 }
 
+// ACA-rect's shape: 32 B in (one array), 36 B out
+__global__ void __launch_bounds__(256) k_mix_rect(const C32* a, C16* h, size_t n)
+{
+    __shared__ __align__(16) uint32_t stage[256 * 9];
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) {
+        C32 x = ld32(a + i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) stage[threadIdx.x * 9 + k] = x.w[k] + 1u;
+        stage[threadIdx.x * 9 + 8] = x.w[0] ^ x.w[7];
+    }
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * 576;
+    for (int c = threadIdx.x; c < 576; c += 256)
+        if (base + c < n * 36 / 16) st16(h + base + c, *reinterpret_cast<C16*>(stage + 4 * c));
+}
+// the fp64 solvers' shape: 128 B in (two arrays of 64 B), 72 B out; 128 quadruples per CTA
+__global__ void __launch_bounds__(128) k_mix_f64(const C32* a, const C32* b, C16* h, size_t n)
+{
+    __shared__ __align__(16) uint32_t stage[128 * 18];
+    size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (i < n) {
+        C32 x0 = ld32(a + 2 * i), x1 = ld32(a + 2 * i + 1), y0 = ld32(b + 2 * i), y1 = ld32(b + 2 * i + 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            stage[threadIdx.x * 18 + k] = x0.w[k] + y0.w[k];
+            stage[threadIdx.x * 18 + 8 + k] = x1.w[k] + y1.w[k];
+        }
+        stage[threadIdx.x * 18 + 16] = x0.w[0] ^ y1.w[7];
+        stage[threadIdx.x * 18 + 17] = x1.w[0] ^ y0.w[7];
+    }
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * 576;           // 128 * 72 / 16 chunks per tile
+    for (int c = threadIdx.x; c < 576; c += 128)
+        if (base + c < n * 72 / 16) st16(h + base + c, *reinterpret_cast<C16*>(stage + 4 * c));
+}
+
 template <typename F>
 float time_ms(F f)
 {
@@ -85,6 +122,13 @@ int main()
     printf("write-only  36 B/thread            %7.3f ms  %7.1f GB/s\n", t, n * 36 / t / 1e6);
     t = time_ms([&] { k_mix<<<grid, 256>>>(a, b, h, n); });
     printf("64 B in + 36 B out, no arithmetic  %7.3f ms  %7.1f GB/s\n", t, n * 100 / t / 1e6);
+    t = time_ms([&] { k_mix_rect<<<grid, 256>>>(a, h, n); });
+    printf("32 B in + 36 B out (ACA-rect)      %7.3f ms  %7.1f GB/s\n", t, n * 68 / t / 1e6);
+    {
+        const size_t n64 = n / 2;                     // 2^25 fp64 quadruples in the same buffers
+        t = time_ms([&] { k_mix_f64<<<(unsigned)(n64 / 128), 128>>>(a, b, h, n64); });
+        printf("128 B in + 72 B out (fp64 solvers) %7.3f ms  %7.1f GB/s\n", t, n64 * 200 / t / 1e6);
+    }
     t = time_ms([&] { cudaMemcpyAsync(h, a, n * 32, cudaMemcpyDeviceToDevice); });
     printf("cudaMemcpy D2D (read+write bytes)  %7.3f ms  %7.1f GB/s\n", t, 2.0 * n * 32 / t / 1e6);
     printf("cudaGetLastError: %s\n", cudaGetErrorString(cudaGetLastError()));
