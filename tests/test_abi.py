@@ -142,3 +142,14 @@ def test_ransac_launch_plan_fills_whole_waves(sks):
     for hyp in (1, 511, 513, 70001):
         c = plan(3, hyp, 384, 4, 3, slots)
         assert c > 0 and c % (384 * 4) == 0
+
+
+def test_sample_list_validation_needs_no_gpu(sks):
+    """api.ransac_keys rejects a mis-typed / mis-sized explicit sample list before anything reaches CUDA."""
+    import torch
+    from sks_homography_b200 import api
+    corr = torch.zeros((2, 50, 4))
+    with pytest.raises(TypeError):
+        api.ransac_keys(corr, 8, 1, 2.25, samples=torch.zeros((2, 8, 4), dtype=torch.int64))
+    with pytest.raises(ValueError):
+        api.ransac_keys(corr, 8, 1, 2.25, samples=torch.zeros((2, 7, 4), dtype=torch.int32))
