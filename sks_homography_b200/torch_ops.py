@@ -8,6 +8,10 @@ sks_homography_b200.api; there is still no CPU compute path.
     torch.ops.sks_b200.ransac(corr, n_hyp, seed, thr2)                -> (H [P,9], count [P], hyp [P])
     torch.ops.sks_b200.rect_warp_grid(tar, M, mx, my, width, ratio, gw, gh, x0, y0, dx, dy)
                                                                       -> grid [n, gh, gw, 2]
+    torch.ops.sks_b200.tensor_aca_rect(src34, tar34, scale, div)      -> H [bs, 3, 3]
+        the reference's TensorACA_rect(bs, src, tar, scale, div) (PY.py:286-309) on its own tensors:
+        [bs,3,4] homogeneous corners, scale / div one-element tensors on the same device -- read by
+        the kernel, so the op neither synchronises nor breaks a torch.compile graph
 "solve" also takes "ge" (the competitor RHO-GE).
 """
 from __future__ import annotations
@@ -64,3 +68,13 @@ def rect_warp_grid(tar: Tensor, M: Tensor | None, mx: float, my: float, width: f
 @rect_warp_grid.register_fake
 def _(tar, M, mx, my, width, ratio, gw, gh, x0, y0, dx, dy):
     return tar.new_empty((tar.numel() // 8, gh, gw, 2))
+
+
+@torch.library.custom_op("sks_b200::tensor_aca_rect", mutates_args=())
+def tensor_aca_rect(src34: Tensor, tar34: Tensor, scale: Tensor, div: Tensor) -> Tensor:
+    return api.TensorACA_rect(tar34.shape[0], src34, tar34, scale, div)
+
+
+@tensor_aca_rect.register_fake
+def _(src34, tar34, scale, div):
+    return tar34.new_empty((tar34.shape[0], 3, 3))

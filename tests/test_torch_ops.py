@@ -23,6 +23,8 @@ def test_ops_are_registered_and_trace_with_fake_tensors(sks):
         G = torch.ops.sks_b200.rect_warp_grid(torch.empty(6, 8), None, 0.0, 0.0, 128.0, 1.0, 16, 12,
                                               0.0, 0.0, 1.0, 1.0)
         assert G.shape == (6, 12, 16, 2)
+        T = torch.ops.sks_b200.tensor_aca_rect(torch.empty(9, 3, 4), torch.empty(9, 3, 4), torch.empty(1), torch.empty(1))
+        assert T.shape == (9, 3, 3) and T.dtype == torch.float32
 
 
 @pytest.mark.gpu
@@ -42,3 +44,16 @@ def test_ops_match_oracle_on_gpu(sks, oracle, cuda):
     torch.library.opcheck(torch.ops.sks_b200.solve.default,
                           (torch.from_numpy(s[:64]).to(cuda), torch.from_numpy(t[:64]).to(cuda), "aca", False),
                           test_utils=("test_schema", "test_faketensor"))
+
+
+@pytest.mark.gpu
+def test_tensor_aca_rect_op_matches_the_reference_golden(sks, golden, cuda):
+    """The reference's TensorACA_rect signature as a registered op: same bits as the golden H obtained by
+    executing the reference's torch statements, scale / div passed as device tensors (no sync), opcheck clean."""
+    import sks_homography_b200.torch_ops  # noqa: F401
+    g = golden["ref_torch"]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    args = (dev(g["src_new"]), dev(g["tar_new"]), dev(g["scale"]), dev(g["div"]))
+    H = torch.ops.sks_b200.tensor_aca_rect(*args)
+    assert_same_bits(H.cpu().numpy(), g["H_rect"], "tensor_aca_rect op")
+    torch.library.opcheck(torch.ops.sks_b200.tensor_aca_rect.default, args, test_utils=("test_schema", "test_faketensor"))
